@@ -31,7 +31,7 @@ extern "C" {
 typedef void* dwm_stream_t; /* cudaStream_t */
 
 enum dwm_dtype { DWM_BF16 = 0, DWM_F16 = 1, DWM_F32 = 2 };
-enum dwm_act { DWM_ACT_NONE = 0, DWM_ACT_GELU_TANH = 1, DWM_ACT_GELU_ERF = 2, DWM_ACT_SILU = 3 };
+enum dwm_act { DWM_ACT_NONE = 0, DWM_ACT_GELU_TANH = 1, DWM_ACT_GELU_ERF = 2, DWM_ACT_SILU = 3, DWM_ACT_RELU = 4 };
 
 /* Epilogues of dwm_b200_linear (all fused into the tcgen05 GEMM kernel). */
 enum dwm_epilogue {
@@ -99,6 +99,120 @@ const char* dwm_b200_last_error(void);
  * PatchEmbed.proj, SD3Transformer2DModel.proj_out; call sites
  * crossview_temporal_dit.py:421-431,517-521,599-600, crossview_temporal.py:562-582). */
 int dwm_b200_linear(const dwm_linear_args* args, dwm_stream_t stream);
+
+/* ---- attention -------------------------------------------------------------------- */
+/* Multi-head softmax attention over GATHERED token groups of the fused q|k|v buffer
+ * produced by DWM_EPI_QKNORM (no permuted copy).  Position j of group (g0,g1,g2) is row
+ *   g0*group_strides[0] + g1*group_strides[1] + g2*group_strides[2]
+ *     + (j / inner) * stride_outer + (j % inner) * stride_inner
+ * q = cols [h*64, h*64+64), k = D + ..., v = 2D + ....  Output rows use the out_* strides;
+ * with split > 0, positions j >= split go to out2 row g*(seq-split) + (j-split)
+ * (context tokens of the joint attention).  mask: uint8 [batches, n_outer, n_outer],
+ * entry [g0 / mask_div, jq / inner, jk / inner] != 0 means "attend".
+ * Replaces F.scaled_dot_product_attention inside diffusers AttnProcessor2_0 /
+ * JointAttnProcessor2_0 and the einops regroupings of
+ * crossview_temporal_dit.py:300-315 (cross-view rowwise + mask expansion) and :335-361
+ * (temporal full / rowwise / pointwise). */
+typedef struct dwm_attention_args {
+  const void* qkv;
+  int64_t ld;
+  int64_t D;
+  int heads;
+  int head_dim; /* must be 64 */
+  int dtype;
+  int64_t group_dims[3];
+  int64_t group_strides[3];
+  int seq;
+  int inner;
+  int64_t stride_outer, stride_inner;
+  void* out;
+  int64_t ldo;
+  int64_t out_group_strides[3];
+  int64_t out_stride_outer, out_stride_inner;
+  int split;
+  void* out2;
+  int64_t ldo2;
+  const unsigned char* mask;
+  int mask_div;
+  int n_outer;
+  float scale;
+} dwm_attention_args;
+
+int dwm_b200_attention(const dwm_attention_args* args, dwm_stream_t stream);
+
+/* ---- row ops ---------------------------------------------------------------------- */
+/* LayerNorm over the last dim of an fp32 residual stream, emitting the 16-bit GEMM operand.
+ *   t = x[m] (+ add_item[m / rows_per_item]) (+ add_full[m]);  if sum_out: sum_out[m] = t
+ *   n = (t - mean) * rsqrt(var + eps) (* weight + bias)
+ *   out[m]  = n * (1 + scale[item]) + shift[item]      (modulation optional)
+ *   out2[m] = n * (1 + scale2[item]) + shift2[item]    (SD35AdaLayerNormZeroX, optional)
+ * Replaces torch.nn.LayerNorm (crossview_temporal.py:545,550,558), AdaLayerNormZero /
+ * AdaLayerNormContinuous modulation and the `hidden_states + view_emb` adds
+ * (crossview_temporal_dit.py:229-230,334,491-494). */
+typedef struct dwm_layernorm_args {
+  int64_t M, D;
+  const float* x;
+  int64_t ldx;
+  const float* add_item; /* [items, add_item_ld] or NULL */
+  int64_t add_item_ld;
+  const float* add_full; /* [M, add_full_ld] or NULL */
+  int64_t add_full_ld;
+  int64_t rows_per_item; /* item(m) = m / rows_per_item (0 => single item) */
+  float* sum_out;        /* optional fp32 [M, ld_sum] */
+  int64_t ld_sum;
+  const float* weight;   /* [D] or NULL */
+  const float* bias;     /* [D] or NULL */
+  float eps;
+  const float* shift;    /* [items, mod_ld] or NULL */
+  const float* scale;
+  const float* shift2;
+  const float* scale2;
+  int64_t mod_ld;
+  void* out;
+  int64_t ldo;
+  void* out2;
+  int64_t ldo2;
+  int dtype;
+} dwm_layernorm_args;
+
+int dwm_b200_layernorm(const dwm_layernorm_args* args, dwm_stream_t stream);
+
+/* out16[i] = act(in32[i]) over n elements (e.g. SiLU(temb) feeding AdaLayerNormZero.linear). */
+int dwm_b200_act_cast(const float* in, void* out, int64_t n, int act, int dtype, dwm_stream_t stream);
+
+/* diffusers Timesteps(num_channels, flip_sin_to_cos, downscale_freq_shift): sinusoidal
+ * embedding of n fp32 scalars -> 16-bit [n, channels] (crossview_temporal_dit.py:153-154,
+ * 163-164, 431-439, 528-532, 559-563). */
+int dwm_b200_sinusoid(const float* t, int64_t n, int channels, int flip_sin_to_cos,
+                      float downscale_freq_shift, void* out, int64_t ldo, int dtype,
+                      dwm_stream_t stream);
+
+/* PatchEmbed im2col: latents [items, C, H, W] (fp32) -> 16-bit [items*(H/p)*(W/p), C*p*p],
+ * column = c*p*p + py*p + px (Conv2d weight flattening), crossview_temporal_dit.py:421. */
+int dwm_b200_patchify(const float* x, int64_t items, int C, int H, int W, int patch, void* out,
+                      int64_t ldo, int dtype, dwm_stream_t stream);
+
+/* Fused tail of one denoising step (ctsd.py:2071-2090 + crossview_temporal_dit.py:603-621 +
+ * temporal_independent.py:176-197): un-patchify the proj_out tokens, classifier-free
+ * guidance combine, per-frame Euler update with INT32 sigma indices, round to the model
+ * dtype like the reference, keep frames outside the schedule range unchanged.
+ *   tokens: fp32 [cfg*B*T*V*S, p*p*C], column = (py*p+px)*C + c, uncond half first
+ *   idx:    int32 [B, T, V];  sigmas: fp32 [n_sigmas];  in_range: uint8 [T]
+ *   latents (in/out): fp32 [B, T, V, C, H, W];  noise_pred (optional out): same shape
+ *   round_dtype: DWM_BF16 / DWM_F16 rounds the updated latent like
+ *   `prev_sample.to(model_output.dtype)`; DWM_F32 keeps fp32. */
+int dwm_b200_cfg_euler_step(const float* tokens, int64_t ld_tok, int cfg, float guidance_scale,
+                            int64_t B, int64_t T, int64_t V, int C, int H, int W, int patch,
+                            const int32_t* idx, const float* sigmas, int n_sigmas,
+                            const unsigned char* in_range, float* latents, float* noise_pred,
+                            int round_dtype, dwm_stream_t stream);
+
+/* FlowMatchEulerDiscreteScheduler.step_by_indices (temporal_independent.py:176-197) on a
+ * latent-layout model output: sample[e] += (sigmas[idx[e/inner]+1] - sigmas[idx[e/inner]]) *
+ * model_output[e], rounded to round_dtype; idx int32 [n/inner]. */
+int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int64_t n,
+                                   int64_t inner, const int32_t* idx, const float* sigmas,
+                                   int n_sigmas, int round_dtype, dwm_stream_t stream);
 
 #ifdef __cplusplus
 }

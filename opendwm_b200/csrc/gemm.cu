@@ -28,7 +28,9 @@ constexpr int B_STAGE_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32x32 fp32)
+constexpr int GEMM_SMEM_BYTES =
+    STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct EpiParams {
   void* out;
@@ -55,6 +57,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     case DWM_ACT_GELU_TANH: return gelu_tanh(v);
     case DWM_ACT_GELU_ERF: return gelu_erf(v);
     case DWM_ACT_SILU: return silu(v);
+    case DWM_ACT_RELU: return fmaxf(v, 0.f);
     default: return v;
   }
 }
@@ -65,196 +68,204 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
-// ---- per-epilogue tile drains (called by the 4 epilogue warps) -----------------
-// `taddr` already contains this warp's lane quarter and the accumulator stage column.
-// `m` is this thread's global row, `n_tile0` the first global column of the tile.
+// ---- tile drain (4 epilogue warps) ----------------------------------------------
+// Each warp owns 32 accumulator rows (TMEM lane quarter).  tcgen05.ld hands every
+// thread one ROW, which would make global accesses 32-way scattered.  So each
+// 32x32 fp32 chunk is transposed through a 4 KB XOR-swizzled shared-memory
+// staging buffer: phase 1 (thread = row) applies the row-local math and dumps,
+// phase 2 (8 lanes per row, float4 per lane, 4 rows per instruction) does the
+// coalesced global traffic (incl. the fp32 residual read-modify-write).
 
-template <typename T>
-__device__ __forceinline__ void epi_store(uint32_t taddr, int m, int M, int n_tile0, int N,
-                                          const EpiParams& p) {
-  long long orow = m;
-  if (p.rows_per_item > 0) {
-    orow = (m / p.rows_per_item) * p.out_item_stride + (m % p.rows_per_item);
-  }
-  orow += p.out_row_offset;
-  T* out = reinterpret_cast<T*>(p.out) + orow * p.ldo;
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int n0 = n_tile0 + c * 32;
-    if (n0 >= N) break;
-    uint32_t r[32];
-    tmem_ld32(taddr + c * 32, r);
-    tmem_ld_wait();
-    if (m < M) {
-      uint32_t pk[16];
+__device__ __forceinline__ void stage_dump(float4* stg, int lane, const float (&v)[32]) {
+  __syncwarp();  // phase-2 readers of the previous chunk are done
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float a = __uint_as_float(r[2 * j]);
-        float b = __uint_as_float(r[2 * j + 1]);
+  for (int j = 0; j < 8; ++j)
+    stg[lane * 8 + (j ^ (lane & 7))] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+}
+
+template <typename T, int EPI>
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, int M,
+                                           int n_tile0, int N, const EpiParams& p, int lane) {
+  constexpr bool kOut16 = (EPI == DWM_EPI_STORE || EPI == DWM_EPI_GEGLU || EPI == DWM_EPI_QKNORM);
+  const int rs = lane >> 3;  // phase-2: row within a group of 4
+  const int c4 = lane & 7;   // phase-2: float4 column within the 32-col chunk
+
+  // phase-2 per-row metadata for the 8 rows this lane stores (it*4 + rs)
+  int orow[8];
+  int rrow[8];
+  int item[8];
+  float alpha[8];
+  const int rpi = static_cast<int>(p.rows_per_item);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int m = m0 + it * 4 + rs;
+    if (m < M) {
+      int o = m;
+      if (kOut16) {
+        if (rpi > 0) o = (m / rpi) * static_cast<int>(p.out_item_stride) + (m % rpi);
+        o += static_cast<int>(p.out_row_offset);
+      }
+      orow[it] = o;
+      if (EPI == DWM_EPI_RESID) {
+        item[it] = rpi > 0 ? m / rpi : 0;
+        rrow[it] = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod) : m;
+        alpha[it] = p.blend_x ? __ldg(p.alpha + (p.rows_per_batch > 0 ? m / static_cast<int>(p.rows_per_batch) : 0)) : 0.f;
+      }
+    } else {
+      orow[it] = -1;
+    }
+  }
+
+  // phase 2 for 16-bit outputs: `ocol` = first output column of the staged chunk
+  auto flush16 = [&](int ocol) {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rs;
+      const float4 v = stg[r * 8 + (c4 ^ (r & 7))];
+      if (orow[it] >= 0) {
+        T* dst = reinterpret_cast<T*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + ocol + c4 * 4;
+        uint2 pk;
+        pk.x = Cvt<T>::pack2(v.x, v.y);
+        pk.y = Cvt<T>::pack2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst) = pk;
+      }
+    }
+  };
+  // phase 2 for fp32 outputs (optionally gated / residual / blended).  The residual
+  // (and blend) operands are prefetched into registers at the top of each chunk so
+  // their HBM latency overlaps the TMEM load + transpose; in-place update is safe
+  // because each lane reads exactly the elements it later writes.
+  float4 rq[8], bq[8];
+  auto prefetch32 = [&](int ocol) {
+    if constexpr (EPI == DWM_EPI_RESID) {
+      const int col = ocol + c4 * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        rq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        bq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (orow[it] >= 0) {
+          if (p.resid) rq[it] = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(rrow[it]) * p.ldr + col);
+          if (p.blend_x) bq[it] = *reinterpret_cast<const float4*>(p.blend_x + static_cast<long long>(orow[it]) * p.ldx + col);
+        }
+      }
+    }
+  };
+  auto flush32 = [&](int ocol) {
+    const int col = ocol + c4 * 4;
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (EPI == DWM_EPI_RESID && p.bias) b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + rs;
+      float4 v = stg[r * 8 + (c4 ^ (r & 7))];
+      if (orow[it] >= 0) {
+        if (EPI == DWM_EPI_RESID) {
+          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+          if (p.gate) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item[it]) * p.gate_ld + col));
+            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+          }
+          v.x += rq[it].x; v.y += rq[it].y; v.z += rq[it].z; v.w += rq[it].w;
+          if (p.blend_x) {
+            const float a = alpha[it], a1 = 1.0f - alpha[it];
+            v.x = a * bq[it].x + a1 * v.x; v.y = a * bq[it].y + a1 * v.y;
+            v.z = a * bq[it].z + a1 * v.z; v.w = a * bq[it].w + a1 * v.w;
+          }
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + col) = v;
+      }
+    }
+  };
+
+  if constexpr (EPI == DWM_EPI_STORE || EPI == DWM_EPI_F32 || EPI == DWM_EPI_RESID) {
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n0 = n_tile0 + c * 32;
+      if (n0 >= N) break;
+      prefetch32(n0);
+      uint32_t r[32];
+      tmem_ld32(taddr + c * 32, r);
+      tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (EPI != DWM_EPI_RESID) {
         if (p.bias) {
-          a += __ldg(p.bias + n0 + 2 * j);
-          b += __ldg(p.bias + n0 + 2 * j + 1);
-        }
-        a = apply_act(a, p.act);
-        b = apply_act(b, p.act);
-        pk[j] = Cvt<T>::pack2(a, b);
-      }
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(out + n0 + 8 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+        }
+        if (p.act != DWM_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+        }
+      }
+      stage_dump(stg, lane, v);
+      if constexpr (EPI == DWM_EPI_STORE) flush16(n0); else flush32(n0);
     }
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void epi_geglu(uint32_t taddr, int m, int M, int n_tile0, int N,
-                                          const EpiParams& p) {
-  // tile columns [0,128) hold the value half, [128,256) the gate half of output
-  // columns [n_tile0/2, n_tile0/2 + 128).
-  T* out = reinterpret_cast<T*>(p.out) + static_cast<long long>(m) * p.ldo + n_tile0 / 2;
+  } else if constexpr (EPI == DWM_EPI_GEGLU) {
+    // tile columns [0,128) hold the value half, [128,256) the gate half of output
+    // columns [n_tile0/2, n_tile0/2 + 128).
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t rv[32], rg[32];
-    tmem_ld32(taddr + c * 32, rv);
-    tmem_ld32(taddr + 128 + c * 32, rg);
-    tmem_ld_wait();
-    if (m < M) {
+    for (int c = 0; c < 4; ++c) {
+      uint32_t rv[32], rg[32];
+      tmem_ld32(taddr + c * 32, rv);
+      tmem_ld32(taddr + 128 + c * 32, rg);
+      tmem_ld_wait();
       const float* bv = p.bias ? p.bias + n_tile0 + c * 32 : nullptr;
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v0 = __uint_as_float(rv[2 * j]), v1 = __uint_as_float(rv[2 * j + 1]);
-        float g0 = __uint_as_float(rg[2 * j]), g1 = __uint_as_float(rg[2 * j + 1]);
-        if (bv) {
-          v0 += __ldg(bv + 2 * j);
-          v1 += __ldg(bv + 2 * j + 1);
-          g0 += __ldg(bv + 128 + 2 * j);
-          g1 += __ldg(bv + 128 + 2 * j + 1);
-        }
-        pk[j] = Cvt<T>::pack2(v0 * gelu_erf(g0), v1 * gelu_erf(g1));
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        st_global_v4(out + c * 32 + 8 * j, pk[4 * j], pk[4 * j + 1], pk[4 * j + 2],
-                     pk[4 * j + 3]);
-    }
-  }
-}
-
-template <typename T>
-__device__ __forceinline__ void epi_qknorm(uint32_t taddr, int m, int M, int n_tile0, int N,
-                                           const EpiParams& p) {
-  long long orow = m;
-  if (p.rows_per_item > 0) {
-    orow = (m / p.rows_per_item) * p.out_item_stride + (m % p.rows_per_item);
-  }
-  orow += p.out_row_offset;
-  T* out = reinterpret_cast<T*>(p.out) + orow * p.ldo;
-#pragma unroll 1
-  for (int g = 0; g < BN / 64; ++g) {
-    const int n0 = n_tile0 + g * 64;
-    if (n0 >= N) break;
-    uint32_t r0[32], r1[32];
-    tmem_ld32(taddr + g * 64, r0);
-    tmem_ld32(taddr + g * 64 + 32, r1);
-    tmem_ld_wait();
-    if (m < M) {
-      float v[64];
+      float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = __uint_as_float(r0[j]);
-        v[32 + j] = __uint_as_float(r1[j]);
+        float a = __uint_as_float(rv[j]);
+        float g = __uint_as_float(rg[j]);
+        if (bv) {
+          a += __ldg(bv + j);
+          g += __ldg(bv + 128 + j);
+        }
+        v[j] = a * gelu_erf(g);
+      }
+      stage_dump(stg, lane, v);
+      flush16(n_tile0 / 2 + c * 32);
+    }
+  } else {  // DWM_EPI_QKNORM: 64-column heads
+#pragma unroll 1
+    for (int g = 0; g < BN / 64; ++g) {
+      const int n0 = n_tile0 + g * 64;
+      if (n0 >= N) break;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr + g * 64, r0);
+      tmem_ld32(taddr + g * 64 + 32, r1);
+      tmem_ld_wait();
+      float v0[32], v1[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v0[j] = __uint_as_float(r0[j]);
+        v1[j] = __uint_as_float(r1[j]);
       }
       if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] += __ldg(p.bias + n0 + j);
+        for (int j = 0; j < 32; ++j) {
+          v0[j] += __ldg(p.bias + n0 + j);
+          v1[j] += __ldg(p.bias + n0 + 32 + j);
+        }
       }
       const int region = n0 / static_cast<int>(p.qk_region);
       if (region < 2) {
         const float* w = region == 0 ? p.qw : p.kw;
         float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 64; ++j) ss += v[j] * v[j];
+        for (int j = 0; j < 32; ++j) ss += v0[j] * v0[j] + v1[j] * v1[j];
         const float inv = rsqrtf(ss * (1.0f / 64.0f) + p.eps);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = v[j] * inv * __ldg(w + j);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        st_global_v4(out + n0 + 8 * j, Cvt<T>::pack2(v[8 * j], v[8 * j + 1]),
-                     Cvt<T>::pack2(v[8 * j + 2], v[8 * j + 3]),
-                     Cvt<T>::pack2(v[8 * j + 4], v[8 * j + 5]),
-                     Cvt<T>::pack2(v[8 * j + 6], v[8 * j + 7]));
-    }
-  }
-}
-
-template <bool kResid>
-__device__ __forceinline__ void epi_f32(uint32_t taddr, int m, int M, int n_tile0, int N,
-                                        const EpiParams& p) {
-  float* out = reinterpret_cast<float*>(p.out) + static_cast<long long>(m) * p.ldo;
-  const float* gate = nullptr;
-  const float* resid = nullptr;
-  const float* bx = nullptr;
-  float alpha = 0.f;
-  if (kResid && m < M) {
-    if (p.gate) {
-      long long item = p.rows_per_item > 0 ? m / p.rows_per_item : 0;
-      gate = p.gate + item * p.gate_ld;
-    }
-    if (p.resid) {
-      long long rr = p.resid_row_mod > 0 ? m % p.resid_row_mod : m;
-      resid = p.resid + rr * p.ldr;
-    }
-    if (p.blend_x) {
-      bx = p.blend_x + static_cast<long long>(m) * p.ldx;
-      alpha = __ldg(p.alpha + (p.rows_per_batch > 0 ? m / p.rows_per_batch : 0));
-    }
-  }
-#pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
-    const int n0 = n_tile0 + c * 32;
-    if (n0 >= N) break;
-    uint32_t r[32];
-    tmem_ld32(taddr + c * 32, r);
-    tmem_ld_wait();
-    if (m < M) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v;
-        v.x = __uint_as_float(r[4 * j]);
-        v.y = __uint_as_float(r[4 * j + 1]);
-        v.z = __uint_as_float(r[4 * j + 2]);
-        v.w = __uint_as_float(r[4 * j + 3]);
-        if (p.bias) {
-          float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4 * j));
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        for (int j = 0; j < 32; ++j) {
+          v0[j] = v0[j] * inv * __ldg(w + j);
+          v1[j] = v1[j] * inv * __ldg(w + 32 + j);
         }
-        if (kResid) {
-          if (gate) {
-            float4 g = __ldg(reinterpret_cast<const float4*>(gate + n0 + 4 * j));
-            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-          }
-          if (resid) {
-            float4 q = *reinterpret_cast<const float4*>(resid + n0 + 4 * j);
-            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-          }
-          if (bx) {
-            float4 x = *reinterpret_cast<const float4*>(bx + n0 + 4 * j);
-            const float b1 = 1.0f - alpha;
-            v.x = alpha * x.x + b1 * v.x;
-            v.y = alpha * x.y + b1 * v.y;
-            v.z = alpha * x.z + b1 * v.z;
-            v.w = alpha * x.w + b1 * v.w;
-          }
-        } else {
-          v.x = apply_act(v.x, p.act);
-          v.y = apply_act(v.y, p.act);
-          v.z = apply_act(v.z, p.act);
-          v.w = apply_act(v.w, p.act);
-        }
-        *reinterpret_cast<float4*>(out + n0 + 4 * j) = v;
       }
+      stage_dump(stg, lane, v0);
+      flush16(n0);
+      stage_dump(stg, lane, v1);
+      flush16(n0 + 32);
     }
   }
 }
@@ -269,7 +280,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float4* epi_stage = reinterpret_cast<float4*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
@@ -371,13 +383,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-      const int m = m_blk * BM + quarter * 32 + lane;
-      const int n_tile0 = n_blk * BN;
-      if constexpr (EPI == DWM_EPI_STORE) epi_store<T>(taddr, m, M, n_tile0, N, p);
-      if constexpr (EPI == DWM_EPI_GEGLU) epi_geglu<T>(taddr, m, M, n_tile0, N, p);
-      if constexpr (EPI == DWM_EPI_QKNORM) epi_qknorm<T>(taddr, m, M, n_tile0, N, p);
-      if constexpr (EPI == DWM_EPI_RESID) epi_f32<true>(taddr, m, M, n_tile0, N, p);
-      if constexpr (EPI == DWM_EPI_F32) epi_f32<false>(taddr, m, M, n_tile0, N, p);
+      drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256, m_blk * BM + quarter * 32, M,
+                         n_blk * BN, N, p, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);

@@ -1,0 +1,313 @@
+// Memory-bound row / elementwise kernels of the CTSD step (sm_100a): LayerNorm with
+// AdaLN modulation (emits the 16-bit GEMM operand), activation casts, sinusoidal
+// embeddings, patchify, and the fused CFG + un-patchify + per-frame Euler update.
+// All are single-pass over HBM with 128-bit accesses.
+#include "common.cuh"
+#include "../../include/dwm_b200.h"
+
+namespace dwm {
+
+// ------------------------------------------------------------------ LayerNorm
+struct LnParams {
+  int M, D;
+  const float* x; long long ldx;
+  const float* add_item; long long add_item_ld;
+  const float* add_full; long long add_full_ld;
+  int rows_per_item;
+  float* sum_out; long long ld_sum;
+  const float* weight; const float* bias; float eps;
+  const float* shift; const float* scale; const float* shift2; const float* scale2; long long mod_ld;
+  void* out; long long ldo; void* out2; long long ldo2;
+};
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 8 + warp;
+  if (m >= p.M) return;
+  const int nvec = p.D >> 2;
+  const int item = p.rows_per_item > 0 ? m / p.rows_per_item : 0;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(m) * p.ldx);
+  const float4* ai = p.add_item ? reinterpret_cast<const float4*>(p.add_item + static_cast<long long>(item) * p.add_item_ld) : nullptr;
+  const float4* af = p.add_full ? reinterpret_cast<const float4*>(p.add_full + static_cast<long long>(m) * p.add_full_ld) : nullptr;
+  float4 v[VPL];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float4 t = xr[idx];
+      if (ai) { const float4 a = __ldg(ai + idx); t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+      if (af) { const float4 a = af[idx]; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+      v[i] = t;
+      sum += t.x + t.y + t.z + t.w;
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (p.sum_out) {
+    float4* so = reinterpret_cast<float4*>(p.sum_out + static_cast<long long>(m) * p.ld_sum);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) so[idx] = v[i];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(p.D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(p.D) + p.eps);
+  const float4* w4 = reinterpret_cast<const float4*>(p.weight);
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias);
+  const float4* sh = p.shift ? reinterpret_cast<const float4*>(p.shift + static_cast<long long>(item) * p.mod_ld) : nullptr;
+  const float4* sc = p.scale ? reinterpret_cast<const float4*>(p.scale + static_cast<long long>(item) * p.mod_ld) : nullptr;
+  const float4* sh2 = p.shift2 ? reinterpret_cast<const float4*>(p.shift2 + static_cast<long long>(item) * p.mod_ld) : nullptr;
+  const float4* sc2 = p.scale2 ? reinterpret_cast<const float4*>(p.scale2 + static_cast<long long>(item) * p.mod_ld) : nullptr;
+  uint2* o1 = reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out) + static_cast<long long>(m) * p.ldo);
+  uint2* o2 = p.out2 ? reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out2) + static_cast<long long>(m) * p.ldo2) : nullptr;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      float4 n;
+      n.x = (v[i].x - mean) * rstd; n.y = (v[i].y - mean) * rstd;
+      n.z = (v[i].z - mean) * rstd; n.w = (v[i].w - mean) * rstd;
+      if (w4) { const float4 w = __ldg(w4 + idx); n.x *= w.x; n.y *= w.y; n.z *= w.z; n.w *= w.w; }
+      if (b4) { const float4 b = __ldg(b4 + idx); n.x += b.x; n.y += b.y; n.z += b.z; n.w += b.w; }
+      float4 y = n;
+      if (sc) { const float4 s = __ldg(sc + idx); y.x *= 1.f + s.x; y.y *= 1.f + s.y; y.z *= 1.f + s.z; y.w *= 1.f + s.w; }
+      if (sh) { const float4 s = __ldg(sh + idx); y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w; }
+      uint2 pk; pk.x = Cvt<T>::pack2(y.x, y.y); pk.y = Cvt<T>::pack2(y.z, y.w);
+      o1[idx] = pk;
+      if (o2) {
+        float4 z = n;
+        if (sc2) { const float4 s = __ldg(sc2 + idx); z.x *= 1.f + s.x; z.y *= 1.f + s.y; z.z *= 1.f + s.z; z.w *= 1.f + s.w; }
+        if (sh2) { const float4 s = __ldg(sh2 + idx); z.x += s.x; z.y += s.y; z.z += s.z; z.w += s.w; }
+        uint2 pk2; pk2.x = Cvt<T>::pack2(z.x, z.y); pk2.y = Cvt<T>::pack2(z.z, z.w);
+        o2[idx] = pk2;
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_ln(const LnParams& p, cudaStream_t s) {
+  const int need = (p.D / 4 + 31) / 32;
+  const unsigned grid = static_cast<unsigned>((p.M + 7) / 8);
+  if (need <= 3) layernorm_kernel<T, 3><<<grid, 256, 0, s>>>(p);
+  else if (need <= 6) layernorm_kernel<T, 6><<<grid, 256, 0, s>>>(p);
+  else if (need <= 12) layernorm_kernel<T, 12><<<grid, 256, 0, s>>>(p);
+  else layernorm_kernel<T, 16><<<grid, 256, 0, s>>>(p);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ act + cast
+template <typename T>
+__global__ void act_cast_kernel(const float* __restrict__ in, T* __restrict__ out, long long n, int act) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    if (act == DWM_ACT_SILU) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+    else if (act == DWM_ACT_GELU_TANH) { v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w); }
+    else if (act == DWM_ACT_GELU_ERF) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+    uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = pk;
+  } else {
+    for (long long k = i; k < n; ++k) {
+      float v = in[k];
+      if (act == DWM_ACT_SILU) v = silu(v);
+      else if (act == DWM_ACT_GELU_TANH) v = gelu_tanh(v);
+      else if (act == DWM_ACT_GELU_ERF) v = gelu_erf(v);
+      out[k] = Cvt<T>::from_f(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ sinusoid
+template <typename T>
+__global__ void sinusoid_kernel(const float* __restrict__ t, long long n, int channels, int flip,
+                                float shift, T* __restrict__ out, long long ldo) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int half = channels / 2;
+  if (i >= n * half) return;
+  const long long r = i / half;
+  const int k = static_cast<int>(i % half);
+  const float freq = expf(-9.210340371976184f * static_cast<float>(k) / (static_cast<float>(half) - shift));
+  const float arg = t[r] * freq;
+  const float sn = sinf(arg), cs = cosf(arg);
+  T* o = out + r * ldo;
+  if (flip) { o[k] = Cvt<T>::from_f(cs); o[half + k] = Cvt<T>::from_f(sn); }
+  else { o[k] = Cvt<T>::from_f(sn); o[half + k] = Cvt<T>::from_f(cs); }
+}
+
+// ------------------------------------------------------------------ patchify
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ x, long long items, int C, int H, int W,
+                                int P, T* __restrict__ out, long long ldo) {
+  const int Hp = H / P, Wp = W / P;
+  const long long total = items * C * H * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  // iterate in OUTPUT order so writes are contiguous: (item, hy, wx, c, py, px)
+  long long r = i;
+  const int px = r % P; r /= P;
+  const int py = r % P; r /= P;
+  const int c = r % C; r /= C;
+  const int wx = r % Wp; r /= Wp;
+  const int hy = r % Hp; r /= Hp;
+  const long long n = r;
+  const float v = x[((n * C + c) * H + hy * P + py) * W + wx * P + px];
+  out[((n * Hp + hy) * Wp + wx) * ldo + (c * P + py) * P + px] = Cvt<T>::from_f(v);
+}
+
+// ------------------------------------------------------------------ CFG + Euler
+__global__ void cfg_euler_kernel(const float* __restrict__ tok, long long ld_tok, int cfg, float gs,
+                                 long long B, long long T, long long V, int C, int H, int W, int P,
+                                 const int* __restrict__ idx, const float* __restrict__ sigmas,
+                                 const unsigned char* __restrict__ in_range,
+                                 float* __restrict__ lat, float* __restrict__ npred, int round_dtype) {
+  const long long total = B * T * V * C * H * W;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int xw = r % W; r /= W;
+  const int yh = r % H; r /= H;
+  const int c = r % C; r /= C;
+  const long long btv = r;  // (b*T + t)*V + v
+  const long long t = (btv / V) % T;
+  const int Hp = H / P, Wp = W / P;
+  const long long S = static_cast<long long>(Hp) * Wp;
+  const long long row = btv * S + (yh / P) * Wp + xw / P;
+  const int col = ((yh % P) * P + xw % P) * C + c;
+  float v = tok[row * ld_tok + col];
+  if (cfg == 2) {
+    const float vc = tok[(row + B * T * V * S) * ld_tok + col];
+    v = v + gs * (vc - v);  // uncond + scale * (cond - uncond)
+  }
+  if (npred) npred[i] = v;
+  const int k = idx[btv];
+  const float dsig = sigmas[k + 1] - sigmas[k];
+  const float old = lat[i];
+  float nv = old + dsig * v;
+  if (round_dtype == DWM_BF16) nv = __bfloat162float(__float2bfloat16_rn(nv));
+  else if (round_dtype == DWM_F16) nv = __half2float(__float2half_rn(nv));
+  lat[i] = (in_range == nullptr || in_range[t]) ? nv : old;
+}
+
+// Per-element Euler update with per-(leading index) sigma indices:
+//   x[e] = round(x[e] + (sigma[idx[e / inner] + 1] - sigma[idx[e / inner]]) * v[e])
+__global__ void euler_idx_kernel(const float* __restrict__ v, float* __restrict__ x, long long n,
+                                 long long inner, const int* __restrict__ idx,
+                                 const float* __restrict__ sigmas, int round_dtype) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = idx[i / inner];
+  float nv = x[i] + (sigmas[k + 1] - sigmas[k]) * v[i];
+  if (round_dtype == DWM_BF16) nv = __bfloat162float(__float2bfloat16_rn(nv));
+  else if (round_dtype == DWM_F16) nv = __half2float(__float2half_rn(nv));
+  x[i] = nv;
+}
+
+}  // namespace dwm
+
+using namespace dwm;
+
+extern "C" int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int64_t n,
+                                              int64_t inner, const int32_t* idx, const float* sigmas,
+                                              int n_sigmas, int round_dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(model_output && sample && idx && sigmas && n > 0 && inner > 0 && n % inner == 0 && n_sigmas > 1,
+              "dwm_b200_euler_step_by_indices: bad arguments");
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  euler_idx_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(model_output, sample, n, inner, idx,
+                                                                            sigmas, round_dtype);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_layernorm(const dwm_layernorm_args* a, dwm_stream_t stream) {
+  DWM_REQUIRE(a != nullptr, "dwm_b200_layernorm: null args");
+  DWM_REQUIRE(a->M > 0 && a->D > 0 && a->M < (1ll << 31), "dwm_b200_layernorm: bad M/D");
+  DWM_REQUIRE(a->D % 4 == 0 && a->D <= 2048, "dwm_b200_layernorm: D must be a multiple of 4 and <= 2048, got %lld", (long long)a->D);
+  DWM_REQUIRE(a->x && a->out, "dwm_b200_layernorm: null x/out");
+  DWM_REQUIRE(a->ldx % 4 == 0 && a->ldo % 4 == 0, "dwm_b200_layernorm: ldx/ldo must be multiples of 4");
+  if (a->shift || a->scale || a->shift2 || a->scale2)
+    DWM_REQUIRE(a->mod_ld % 4 == 0, "dwm_b200_layernorm: mod_ld must be a multiple of 4");
+  LnParams p;
+  p.M = static_cast<int>(a->M); p.D = static_cast<int>(a->D);
+  p.x = a->x; p.ldx = a->ldx;
+  p.add_item = a->add_item; p.add_item_ld = a->add_item_ld;
+  p.add_full = a->add_full; p.add_full_ld = a->add_full_ld;
+  p.rows_per_item = static_cast<int>(a->rows_per_item);
+  p.sum_out = a->sum_out; p.ld_sum = a->ld_sum;
+  p.weight = a->weight; p.bias = a->bias; p.eps = a->eps;
+  p.shift = a->shift; p.scale = a->scale; p.shift2 = a->shift2; p.scale2 = a->scale2; p.mod_ld = a->mod_ld;
+  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->dtype == DWM_BF16) return launch_ln<__nv_bfloat16>(p, s);
+  if (a->dtype == DWM_F16) return launch_ln<__half>(p, s);
+  set_last_error("dwm_b200_layernorm: dtype must be DWM_BF16 or DWM_F16");
+  return -1;
+}
+
+extern "C" int dwm_b200_act_cast(const float* in, void* out, int64_t n, int act, int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(in && out && n > 0, "dwm_b200_act_cast: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned grid = static_cast<unsigned>((n / 4 + 1 + 255) / 256);
+  if (dtype == DWM_BF16) act_cast_kernel<<<grid, 256, 0, s>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n, act);
+  else if (dtype == DWM_F16) act_cast_kernel<<<grid, 256, 0, s>>>(in, reinterpret_cast<__half*>(out), n, act);
+  else { set_last_error("dwm_b200_act_cast: bad dtype"); return -1; }
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_sinusoid(const float* t, int64_t n, int channels, int flip, float shift,
+                                 void* out, int64_t ldo, int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(t && out && n > 0 && channels > 0 && channels % 2 == 0, "dwm_b200_sinusoid: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = n * (channels / 2);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == DWM_BF16) sinusoid_kernel<<<grid, 256, 0, s>>>(t, n, channels, flip, shift, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  else if (dtype == DWM_F16) sinusoid_kernel<<<grid, 256, 0, s>>>(t, n, channels, flip, shift, reinterpret_cast<__half*>(out), ldo);
+  else { set_last_error("dwm_b200_sinusoid: bad dtype"); return -1; }
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_patchify(const float* x, int64_t items, int C, int H, int W, int patch,
+                                 void* out, int64_t ldo, int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(x && out && items > 0 && patch > 0 && H % patch == 0 && W % patch == 0, "dwm_b200_patchify: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = items * C * H * W;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == DWM_BF16) patchify_kernel<<<grid, 256, 0, s>>>(x, items, C, H, W, patch, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  else if (dtype == DWM_F16) patchify_kernel<<<grid, 256, 0, s>>>(x, items, C, H, W, patch, reinterpret_cast<__half*>(out), ldo);
+  else { set_last_error("dwm_b200_patchify: bad dtype"); return -1; }
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_cfg_euler_step(const float* tokens, int64_t ld_tok, int cfg, float guidance_scale,
+                                       int64_t B, int64_t T, int64_t V, int C, int H, int W, int patch,
+                                       const int32_t* idx, const float* sigmas, int n_sigmas,
+                                       const unsigned char* in_range, float* latents, float* noise_pred,
+                                       int round_dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(tokens && idx && sigmas && latents, "dwm_b200_cfg_euler_step: null pointer");
+  DWM_REQUIRE(cfg == 1 || cfg == 2, "dwm_b200_cfg_euler_step: cfg must be 1 or 2");
+  DWM_REQUIRE(B > 0 && T > 0 && V > 0 && C > 0 && patch > 0 && H % patch == 0 && W % patch == 0 && n_sigmas > 1,
+              "dwm_b200_cfg_euler_step: bad shape");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = B * T * V * C * H * W;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  cfg_euler_kernel<<<grid, 256, 0, s>>>(tokens, ld_tok, cfg, guidance_scale, B, T, V, C, H, W, patch, idx,
+                                        sigmas, in_range, latents, noise_pred, round_dtype);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

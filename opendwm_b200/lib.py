@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdwm_b200.so")
 
 DWM_BF16, DWM_F16, DWM_F32 = 0, 1, 2
-ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF, ACT_SILU, ACT_RELU = 0, 1, 2, 3, 4
 EPI_STORE, EPI_GEGLU, EPI_QKNORM, EPI_RESID, EPI_F32 = 0, 1, 2, 3, 4
 
 _i64 = ctypes.c_int64
@@ -37,6 +37,39 @@ class LinearArgs(ctypes.Structure):
     ]
 
 
+class AttentionArgs(ctypes.Structure):
+    _fields_ = [
+        ("qkv", _p), ("ld", _i64), ("D", _i64),
+        ("heads", ctypes.c_int), ("head_dim", ctypes.c_int),
+        ("dtype", ctypes.c_int),
+        ("group_dims", _i64 * 3), ("group_strides", _i64 * 3),
+        ("seq", ctypes.c_int), ("inner", ctypes.c_int),
+        ("stride_outer", _i64), ("stride_inner", _i64),
+        ("out", _p), ("ldo", _i64),
+        ("out_group_strides", _i64 * 3),
+        ("out_stride_outer", _i64), ("out_stride_inner", _i64),
+        ("split", ctypes.c_int), ("out2", _p), ("ldo2", _i64),
+        ("mask", _p), ("mask_div", ctypes.c_int), ("n_outer", ctypes.c_int),
+        ("scale", ctypes.c_float),
+    ]
+
+
+class LayerNormArgs(ctypes.Structure):
+    _fields_ = [
+        ("M", _i64), ("D", _i64),
+        ("x", _p), ("ldx", _i64),
+        ("add_item", _p), ("add_item_ld", _i64),
+        ("add_full", _p), ("add_full_ld", _i64),
+        ("rows_per_item", _i64),
+        ("sum_out", _p), ("ld_sum", _i64),
+        ("weight", _p), ("bias", _p), ("eps", ctypes.c_float),
+        ("shift", _p), ("scale", _p), ("shift2", _p), ("scale2", _p),
+        ("mod_ld", _i64),
+        ("out", _p), ("ldo", _i64), ("out2", _p), ("ldo2", _i64),
+        ("dtype", ctypes.c_int),
+    ]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/dwm_b200.h declares.
@@ -44,6 +77,20 @@ SYMBOLS = {
     "dwm_b200_version": (ctypes.c_char_p, []),
     "dwm_b200_last_error": (ctypes.c_char_p, []),
     "dwm_b200_linear": (ctypes.c_int, [ctypes.POINTER(LinearArgs), _p]),
+    "dwm_b200_attention": (ctypes.c_int, [ctypes.POINTER(AttentionArgs), _p]),
+    "dwm_b200_layernorm": (ctypes.c_int, [ctypes.POINTER(LayerNormArgs), _p]),
+    "dwm_b200_act_cast": (ctypes.c_int, [_p, _p, _i64, ctypes.c_int, ctypes.c_int, _p]),
+    "dwm_b200_sinusoid": (ctypes.c_int, [_p, _i64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_float, _p, _i64, ctypes.c_int, _p]),
+    "dwm_b200_patchify": (ctypes.c_int, [_p, _i64, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_int, _p, _i64,
+                                         ctypes.c_int, _p]),
+    "dwm_b200_cfg_euler_step": (ctypes.c_int, [
+        _p, _i64, ctypes.c_int, ctypes.c_float, _i64, _i64, _i64, ctypes.c_int,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, _p, _p, ctypes.c_int, _p, _p,
+        _p, ctypes.c_int, _p]),
+    "dwm_b200_euler_step_by_indices": (ctypes.c_int, [
+        _p, _p, _i64, _i64, _p, _p, ctypes.c_int, ctypes.c_int, _p]),
 }
 
 

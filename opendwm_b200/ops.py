@@ -111,3 +111,166 @@ def pack_geglu(weight: torch.Tensor, bias=None, block=128):
     w = weight.index_select(0, idx).contiguous()
     b = None if bias is None else bias.index_select(0, idx).contiguous()
     return w, b
+
+
+def _code(dtype):
+    if dtype == torch.bfloat16:
+        return _l.DWM_BF16
+    if dtype == torch.float16:
+        return _l.DWM_F16
+    if dtype == torch.float32:
+        return _l.DWM_F32
+    raise TypeError("unsupported dtype {}".format(dtype))
+
+
+def attention(qkv, out, *, D, heads, group_dims, group_strides, seq, inner=None,
+              stride_outer=0, stride_inner=1, out_group_strides=None,
+              out_stride_outer=None, out_stride_inner=None, split=0, out2=None,
+              mask=None, mask_div=1, scale=None):
+    """Gathered multi-head attention over the fused q|k|v buffer; see
+    dwm_attention_args in include/dwm_b200.h."""
+    _rows2d(qkv, "qkv")
+    _rows2d(out, "out")
+    if not qkv.is_cuda:
+        raise RuntimeError("dwm_b200 kernels need CUDA tensors (no CPU fallback)")
+    a = _l.AttentionArgs()
+    a.qkv, a.ld, a.D = qkv.data_ptr(), qkv.stride(0), D
+    a.heads, a.head_dim, a.dtype = heads, D // heads, _dt(qkv)
+    gd = list(group_dims) + [1] * (3 - len(group_dims))
+    gs = list(group_strides) + [0] * (3 - len(group_strides))
+    ogs = gs if out_group_strides is None else \
+        list(out_group_strides) + [0] * (3 - len(out_group_strides))
+    for i in range(3):
+        a.group_dims[i], a.group_strides[i], a.out_group_strides[i] = \
+            gd[i], gs[i], ogs[i]
+    a.seq, a.inner = seq, seq if inner is None else inner
+    a.stride_outer, a.stride_inner = stride_outer, stride_inner
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.out_stride_outer = stride_outer if out_stride_outer is None \
+        else out_stride_outer
+    a.out_stride_inner = stride_inner if out_stride_inner is None \
+        else out_stride_inner
+    a.split = split
+    if out2 is not None:
+        _rows2d(out2, "out2")
+        a.out2, a.ldo2 = out2.data_ptr(), out2.stride(0)
+    if mask is not None:
+        if mask.dtype != torch.uint8 or mask.dim() != 3 or not mask.is_contiguous():
+            raise TypeError("mask must be a contiguous uint8 [B, n, n] tensor")
+        a.mask, a.mask_div, a.n_outer = mask.data_ptr(), mask_div, mask.shape[-1]
+    a.scale = (D // heads) ** -0.5 if scale is None else scale
+    _l.check(_l.load().dwm_b200_attention(ctypes.byref(a), _stream()),
+             "dwm_b200_attention")
+    return out
+
+
+def layernorm(x, out, *, weight=None, bias=None, eps=1e-5, add_item=None,
+              add_full=None, rows_per_item=0, sum_out=None, shift=None,
+              scale=None, shift2=None, scale2=None, out2=None):
+    """LayerNorm (+adds, +AdaLN modulation) of an fp32 stream into 16-bit out."""
+    _rows2d(_f32(x, "x"), "x")
+    _rows2d(out, "out")
+    a = _l.LayerNormArgs()
+    a.M, a.D = x.shape
+    a.x, a.ldx = x.data_ptr(), x.stride(0)
+    if add_item is not None:
+        _rows2d(_f32(add_item, "add_item"), "add_item")
+        a.add_item, a.add_item_ld = add_item.data_ptr(), add_item.stride(0)
+    if add_full is not None:
+        _rows2d(_f32(add_full, "add_full"), "add_full")
+        a.add_full, a.add_full_ld = add_full.data_ptr(), add_full.stride(0)
+    a.rows_per_item = rows_per_item
+    if sum_out is not None:
+        _rows2d(_f32(sum_out, "sum_out"), "sum_out")
+        a.sum_out, a.ld_sum = sum_out.data_ptr(), sum_out.stride(0)
+    a.weight, a.bias, a.eps = _ptr(_f32(weight, "weight")), _ptr(_f32(bias, "bias")), eps
+    mod_ld = None
+    for name, t in (("shift", shift), ("scale", scale), ("shift2", shift2),
+                    ("scale2", scale2)):
+        if t is not None:
+            _rows2d(_f32(t, name), name)
+            if mod_ld is not None and t.stride(0) != mod_ld:
+                raise ValueError("modulation tensors must share a row pitch")
+            mod_ld = t.stride(0)
+            setattr(a, name, t.data_ptr())
+    a.mod_ld = mod_ld or 0
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        _rows2d(out2, "out2")
+        a.out2, a.ldo2 = out2.data_ptr(), out2.stride(0)
+    a.dtype = _dt(out)
+    _l.check(_l.load().dwm_b200_layernorm(ctypes.byref(a), _stream()),
+             "dwm_b200_layernorm")
+    return out
+
+
+def act_cast(x, out, act=_l.ACT_NONE):
+    _f32(x, "x")
+    if not x.is_contiguous() or not out.is_contiguous():
+        raise ValueError("act_cast needs contiguous tensors")
+    _l.check(_l.load().dwm_b200_act_cast(
+        x.data_ptr(), out.data_ptr(), x.numel(), act, _dt(out), _stream()),
+        "dwm_b200_act_cast")
+    return out
+
+
+def sinusoid(t, channels, out, flip_sin_to_cos=True, downscale_freq_shift=0.0):
+    _f32(t, "t")
+    _rows2d(out, "out")
+    _l.check(_l.load().dwm_b200_sinusoid(
+        t.data_ptr(), t.numel(), channels, int(flip_sin_to_cos),
+        float(downscale_freq_shift), out.data_ptr(), out.stride(0), _dt(out),
+        _stream()), "dwm_b200_sinusoid")
+    return out
+
+
+def patchify(x, patch, out):
+    _f32(x, "x")
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("x must be contiguous [items, C, H, W]")
+    _rows2d(out, "out")
+    n, c, h, w = x.shape
+    _l.check(_l.load().dwm_b200_patchify(
+        x.data_ptr(), n, c, h, w, patch, out.data_ptr(), out.stride(0),
+        _dt(out), _stream()), "dwm_b200_patchify")
+    return out
+
+
+def cfg_euler_step(tokens, latents, idx, sigmas, *, cfg, guidance_scale, patch,
+                   in_range=None, noise_pred=None, round_dtype=torch.float32):
+    _rows2d(_f32(tokens, "tokens"), "tokens")
+    _f32(latents, "latents")
+    _f32(sigmas, "sigmas")
+    if latents.dim() != 6 or not latents.is_contiguous():
+        raise ValueError("latents must be contiguous [B,T,V,C,H,W]")
+    if idx.dtype != torch.int32 or not idx.is_contiguous():
+        raise TypeError("idx must be contiguous int32 [B,T,V]")
+    if in_range is not None and (in_range.dtype != torch.uint8 or
+                                 in_range.numel() != latents.shape[1]):
+        raise TypeError("in_range must be uint8 [T]")
+    B, T, V, C, H, W = latents.shape
+    _l.check(_l.load().dwm_b200_cfg_euler_step(
+        tokens.data_ptr(), tokens.stride(0), cfg, float(guidance_scale),
+        B, T, V, C, H, W, patch, idx.data_ptr(), sigmas.data_ptr(),
+        sigmas.numel(), _ptr(in_range), latents.data_ptr(), _ptr(noise_pred),
+        _code(round_dtype), _stream()), "dwm_b200_cfg_euler_step")
+    return latents
+
+
+def euler_step_by_indices(model_output, sample, idx, sigmas, round_dtype=torch.float32):
+    """sample (fp32, in place) += dsigma[idx] * model_output; idx int32 over the
+    leading dims of sample."""
+    _f32(model_output, "model_output")
+    _f32(sample, "sample")
+    _f32(sigmas, "sigmas")
+    if not (model_output.is_contiguous() and sample.is_contiguous() and idx.is_contiguous()):
+        raise ValueError("euler_step_by_indices needs contiguous tensors")
+    if idx.dtype != torch.int32:
+        raise TypeError("idx must be int32")
+    n = sample.numel()
+    inner = n // idx.numel()
+    _l.check(_l.load().dwm_b200_euler_step_by_indices(
+        model_output.data_ptr(), sample.data_ptr(), n, inner, idx.data_ptr(),
+        sigmas.data_ptr(), sigmas.numel(), _code(round_dtype), _stream()),
+        "dwm_b200_euler_step_by_indices")
+    return sample

@@ -1,0 +1,106 @@
+"""Parity of the gathered attention kernel against fp32 softmax(QK^T)V on the same
+16-bit q|k|v, for every regrouping the CTSD DiT uses."""
+import itertools
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _qkv(rows, D, dtype, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(rows, 3 * D, generator=g).to(dtype).cuda()
+
+
+def _ref(qkv, rows_idx, D, heads, mask=None):
+    """rows_idx: long [G, seq]; mask: bool [G, seq, seq] or None -> fp32 [G, seq, D]."""
+    G, seq = rows_idx.shape
+    x = qkv.float()[rows_idx.reshape(-1)].view(G, seq, 3, heads, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2) * 0.125
+    if mask is not None:
+        s = s.masked_fill(~mask[:, None], float("-inf"))
+    return (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(G, seq, D)
+
+
+def _tol(dtype):
+    return 1.2e-2 if dtype == torch.bfloat16 else 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_joint_split(dtype):
+    from opendwm_b200 import ops
+    N, S, L, heads = 3, 448, 154, 3
+    D = heads * 64
+    qkv = _qkv(N * (S + L), D, dtype)
+    out = torch.zeros(N * S, D, dtype=dtype, device="cuda")
+    out2 = torch.zeros(N * L, D, dtype=dtype, device="cuda")
+    ops.attention(qkv, out, D=D, heads=heads, group_dims=[N], group_strides=[S + L],
+                  seq=S + L, out_group_strides=[S], out_stride_outer=0, out_stride_inner=1,
+                  split=S, out2=out2)
+    idx = torch.arange(N * (S + L), device="cuda").view(N, S + L)
+    ref = _ref(qkv, idx, D, heads)
+    err = (out.view(N, S, D).float() - ref[:, :S]).abs().max() / ref.abs().max()
+    err2 = (out2.view(N, L, D).float() - ref[:, S:]).abs().max() / ref.abs().max()
+    assert err < _tol(dtype) and err2 < _tol(dtype), (err, err2)
+
+
+@pytest.mark.parametrize("use_mask", [False, True])
+def test_crossview_rowwise(use_mask):
+    from opendwm_b200 import ops
+    B, T, V, H, W, heads = 2, 2, 6, 4, 28, 2
+    S, D, dtype = H * W, heads * 64, torch.bfloat16
+    qkv = _qkv(B * T * V * S, D, dtype)
+    out = torch.zeros(B * T * V * S, D, dtype=dtype, device="cuda")
+    ring = torch.zeros(V, V, dtype=torch.bool)
+    for i in range(V):
+        for d in (-1, 0, 1):
+            ring[i, (i + d) % V] = True
+    m = torch.stack([ring, torch.ones(V, V, dtype=torch.bool)]).cuda()  # batch 1 unmasked
+    ops.attention(qkv, out, D=D, heads=heads, group_dims=[B * T, H], group_strides=[V * S, W],
+                  seq=V * W, inner=W, stride_outer=S, stride_inner=1,
+                  mask=m.to(torch.uint8).contiguous() if use_mask else None, mask_div=T)
+    bt, h, v, w = torch.meshgrid(torch.arange(B * T), torch.arange(H), torch.arange(V),
+                                 torch.arange(W), indexing="ij")
+    idx = ((bt * V + v) * S + h * W + w).view(B * T * H, V * W).cuda()
+    mask = None
+    if use_mask:
+        mask = m.repeat_interleave(W, 2).repeat_interleave(W, 1).repeat_interleave(T * H, 0)
+    ref = _ref(qkv, idx, D, heads, mask)
+    got = out.float()[idx.reshape(-1)].view(B * T * H, V * W, D)
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < _tol(dtype)
+
+
+@pytest.mark.parametrize("T,kind", [(16, "pointwise"), (19, "pointwise"), (5, "pointwise"),
+                                    (5, "rowwise"), (3, "full")])
+def test_temporal(T, kind):
+    from opendwm_b200 import ops
+    B, V, H, W, heads = 2, 2, 2, 6, 2
+    S, D, dtype = H * W, heads * 64, torch.bfloat16
+    qkv = _qkv(B * T * V * S, D, dtype, seed=T)
+    out = torch.zeros(B * T * V * S, D, dtype=dtype, device="cuda")
+    if kind == "pointwise":   # (b v hw) t
+        ops.attention(qkv, out, D=D, heads=heads, group_dims=[B, V * S],
+                      group_strides=[T * V * S, 1], seq=T, inner=1, stride_outer=V * S,
+                      stride_inner=0)
+        b, r, t = torch.meshgrid(torch.arange(B), torch.arange(V * S), torch.arange(T), indexing="ij")
+        idx = (b * T * V * S + t * V * S + r).view(B * V * S, T)
+    elif kind == "rowwise":   # (b v h) (t w)
+        ops.attention(qkv, out, D=D, heads=heads, group_dims=[B, V, H],
+                      group_strides=[T * V * S, S, W], seq=T * W, inner=W, stride_outer=V * S,
+                      stride_inner=1)
+        b, v, h, t, w = torch.meshgrid(torch.arange(B), torch.arange(V), torch.arange(H),
+                                       torch.arange(T), torch.arange(W), indexing="ij")
+        idx = (((b * T + t) * V + v) * S + h * W + w).view(B * V * H, T * W)
+    else:                     # (b v) (t hw)
+        ops.attention(qkv, out, D=D, heads=heads, group_dims=[B, V],
+                      group_strides=[T * V * S, S], seq=T * S, inner=S, stride_outer=V * S,
+                      stride_inner=1)
+        b, v, t, s = torch.meshgrid(torch.arange(B), torch.arange(V), torch.arange(T),
+                                    torch.arange(S), indexing="ij")
+        idx = (((b * T + t) * V + v) * S + s).view(B * V, T * S)
+    idx = idx.cuda()
+    ref = _ref(qkv, idx, D, heads)
+    got = out.float()[idx.reshape(-1)].view(*idx.shape, D)
+    assert ((got - ref).abs().max() / ref.abs().max()).item() < _tol(dtype)
