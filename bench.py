@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""Benchmark of the CTSD-3.5 diffusion-forcing denoise step (BASELINE.json metric:
+denoise-steps/sec, 6 views x 16 frames, CFG on).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo (sm_100a kernels)
+  python bench.py --impl reference --steps K --warmup W    # reference semantics on host CPU
+
+One "step" = one iteration of StreamingCrossviewTemporalSD.inference_pipeline's loop
+(reference ctsd.py:2046-2090): CFG-doubled noise-predict forward on latents
+[2,16,6,16,32,56], CFG combine, per-frame Euler update, masked latent update, at the
+steady-state diffusion-forcing indices i in {45,46,47} of a 48-step schedule.
+Synthetic inputs (seed 0) and random-init weights N(0, 0.02) of the north-star
+architecture (no checkpoints / datasets offline).
+
+Multi-GPU (torchrun, one rank per GPU): the 6xT view-frame grid x CFG branch is
+sharded: first over the two CFG branches, then over frames; strong scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "src")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "CTSD-3.5 6view x 16f denoise-steps/sec"
+F_STEP_TFLOP = 396.2   # algorithmic FLOPs per step, SURVEY.md §8(d) / tools/flops.py
+
+
+def load_config(small=False):
+    with open(os.path.join(ROOT, "configs", "ctsd_35_df16_northstar.json")) as f:
+        cfg = json.load(f)
+    if small:
+        m = cfg["model"]
+        m.update(num_layers=4, dual_attention_layers=[0, 1],
+                 crossview_block_layers=[1], temporal_block_layers=[2, 3],
+                 pos_embed_max_size=96)
+        cfg["latent_shape"] = [1, 4, 6, 16, 16, 24]
+        cfg["text_tokens"] = 20
+        cfg["inference_steps"] = 12
+    return cfg
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs"), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def synthetic_conditions(cfg, B_cfg, T, V, device, dtype, seed=0):
+    """SURVEY.md §8(d) synthetic inputs; B_cfg = CFG-doubled batch (uncond first)."""
+    m = cfg["model"]
+    g = torch.Generator().manual_seed(seed)
+    L = cfg["text_tokens"]
+    H, W = cfg["latent_shape"][-2:]
+    ehs = (torch.randn(B_cfg, T, V, L, m["joint_attention_dim"], generator=g) * 0.1)
+    pooled = torch.randn(B_cfg, T, V, m["pooled_projection_dim"], generator=g)
+    img = torch.rand(B_cfg, T, V, 6, H * 8, W * 8, generator=g)
+    ids = torch.randn(B_cfg, T, V, 13, generator=g)
+    ids[..., 0] = 10.0                                   # fps
+    ids[..., 11] = torch.rand(B_cfg, T, V, generator=g) * 60   # speed km/h
+    ids[..., 12] = torch.randn(B_cfg, T, V, generator=g) * 30  # steering
+    half = B_cfg // 2
+    if half:
+        img[:half] = 0.1255                               # uncondition_image_color
+        ids[:half, ..., 11:] = -1000.0
+        ids[half:, ..., :11] = ids[:half, ..., :11]
+    ring = torch.zeros(V, V, dtype=torch.bool)
+    for i in range(V):
+        for d in (-1, 0, 1):
+            ring[i, (i + d) % V] = True
+    return dict(
+        encoder_hidden_states=ehs.to(device=device, dtype=dtype),
+        pooled_projections=pooled.to(device=device, dtype=dtype),
+        condition_image_tensor=img.to(device=device, dtype=dtype),
+        disable_crossview=torch.zeros(B_cfg, dtype=torch.bool, device=device),
+        disable_temporal=torch.zeros(B_cfg, dtype=torch.bool, device=device),
+        crossview_attention_mask=ring.unsqueeze(0).repeat(B_cfg, 1, 1).to(device),
+        added_time_ids=ids.to(device))
+
+
+def init_weights_(model, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("mix_factor"):
+                continue
+            if p.dim() == 1 and name.endswith(".weight"):
+                p.fill_(1.0)
+            elif name.endswith(".bias"):
+                p.zero_()
+            else:
+                p.copy_(torch.randn(p.shape, generator=g, device="cuda",
+                                    dtype=torch.float32).mul_(0.02).to(p.dtype))
+
+
+# ----------------------------------------------------------------------------- native arm
+def run_native(args):
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import StreamingCrossviewTemporalSD
+    from opendwm_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    cfg = load_config(args.small)
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
+    B, T, V, C, H, W = cfg["latent_shape"]
+    steps = cfg["inference_steps"]
+    spi = steps // T
+
+    from opendwm_b200.sharding import ShardPlan
+    plan = ShardPlan(world, rank, T, cfg=True) if world > 1 else None
+    cfg_ways = plan.cfg_ways if plan else 1
+    t_ways = plan.t_ways if plan else 1
+
+    torch.set_default_dtype(dtype)
+    with torch.device(dev):
+        model = DiTCrossviewTemporalConditionModel(**cfg["model"], compute_dtype=dtype)
+    torch.set_default_dtype(torch.float32)
+    init_weights_(model)
+    pipe_cfg = {"generator_seed": 0}
+    common = {"frame_prediction_style": "diffusion_forcing"}
+    inf = {"guidance_scale": cfg["guidance_scale"], "inference_steps": steps,
+           "sequence_length_per_iteration": T,
+           "scheduler": "dwm.schedulers.temporal_independent."
+                        "FlowMatchEulerDiscreteScheduler"}
+    pipe = StreamingCrossviewTemporalSD(
+        None, pipe_cfg, dev, common, {}, inf, None, model, model_dtype=dtype)
+    pipe.reset_streaming((B, T, V, C, H, W), "pt")
+
+    pipe.sharding = plan
+    cond_full = synthetic_conditions(cfg, 2 * B, T, V, dev, dtype)
+    gen = torch.Generator().manual_seed(0)
+    latents_full = torch.randn(B, T, V, C, H, W, generator=gen)
+    if plan is not None:     # this rank's CFG branch / frames, sliced ONCE
+        cond = plan.local_conditions(cond_full, cfg_doubled=True)
+        latents_host = plan.local_latents(latents_full).pin_memory()
+        fs = plan.frame_slice()
+    else:
+        cond, latents_host, fs = cond_full, latents_full.pin_memory(), slice(0, T)
+    del cond_full
+    latents = latents_host.to(dev)
+
+    def step_tensors(i):
+        idx, ts, in_range = pipe._df_step_tensors(i, T, spi, 0, B, V)
+        return (idx[:, fs].contiguous(), ts[:, fs].contiguous(), in_range[fs].contiguous())
+
+    idx_list = [step_tensors(i) for i in (steps - 3, steps - 2, steps - 1)]
+
+    def one_step(k, lat):
+        idx, ts, in_range = idx_list[k % 3]
+        pipe.denoise_step(lat, cond, idx, ts, in_range)
+
+    lat_dev = torch.empty_like(latents)
+    idx_dev = torch.empty_like(idx_list[0][0])
+
+    def step_host(src_host, dst_host, idx_host, k):
+        """End-to-end step: pinned host latents + indices in, updated latents out."""
+        lat_dev.copy_(src_host, non_blocking=True)
+        idx_dev.copy_(idx_host, non_blocking=True)
+        _, ts, in_range = idx_list[k % 3]
+        pipe.denoise_step(lat_dev, cond, idx_dev, ts, in_range)
+        dst_host.copy_(lat_dev, non_blocking=True)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        one_step(k, latents)
+    sync()
+
+    # ---- timed region: device-resident inputs -----------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for k in range(args.steps):
+        one_step(k, latents)
+    e1.record()
+    sync()
+    prof = ops.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+
+    # ---- end-to-end: host latents in, host latents out, every step --------------------
+    out_host = torch.empty_like(latents_host).pin_memory()
+    idx_host = [t[0].cpu().pin_memory() for t in idx_list]
+    for k in range(2):
+        step_host(latents_host, out_host, idx_host[k % 3], k)
+    sync()
+    e0.record()
+    for k in range(args.steps):
+        step_host(latents_host, out_host, idx_host[k % 3], k)
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_e2e = t.item()
+
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
+    peak_tf, peak_hbm, peak_src = peaks()
+    gemm_ms = sum(p["ms"] for p in prof["linear"])
+    gemm_fl = sum(p["flops"] for p in prof["linear"])
+    n_gemm = len(prof["linear"])
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    scale = 1.0 if not args.small else None
+    line = {
+        "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {
+            "workload": "ctsd_35 DFoT 6-view x 16-frame with layout "
+                        "(examples/ctsd_35_df16_6views_video_generation_with_layout.json)"
+                        + (" [--small debug shape]" if args.small else ""),
+            "latent_shape": [2 * B, T, V, C, H, W], "cfg": True,
+            "df_indices": [steps - 3, steps - 2, steps - 1], "inference_steps": steps,
+            "weights": "random N(0,0.02)", "parallelism":
+                "cfg%dxframes%d" % (cfg_ways, t_ways),
+            "l2": "inputs larger than L2 (7.4 GB weights + >5 GB activations per step)",
+            "step_flops_tflop": F_STEP_TFLOP if scale else None},
+        "roofline": {
+            "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+            "kernel": "gemm_tcgen05_kernel (all dwm_b200_linear launches of the timed "
+                      "steps, CUDA events per launch)",
+            "launches": n_gemm, "gemm_share_of_step": gemm_ms / (ms * args.steps),
+            "peak_source": peak_src + " bf16_tflops_sustained",
+            "step_frac_of_peak": (F_STEP_TFLOP / world / (ms * 1e-3) / peak_tf)
+            if scale else None},
+        "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s",
+                "h2d_bytes_per_step": latents_host.numel() * 4 + idx_host[0].numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4,
+                "api": "StreamingCrossviewTemporalSD.denoise_step with pinned host "
+                       "latents + index tensors copied in and latents copied out"},
+        "gpu_launches": prof["launches"],
+        "clocks": clocks,
+    }
+    if args.profile_dump:
+        agg = {}
+        for p_ in prof["linear"]:
+            k = (tuple(p_["shape"]), p_["epilogue"])
+            a = agg.setdefault(k, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += p_["ms"]
+            a[2] += p_["flops"]
+        rows = [{"M": k[0][0], "N": k[0][1], "K": k[0][2], "epilogue": k[1],
+                 "launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps,
+                 "tflops": v[2] / v[1] / 1e9} for k, v in agg.items()]
+        rows.sort(key=lambda r: -r["ms_per_step"])
+        with open(args.profile_dump, "w") as f:
+            json.dump({"ms_per_step": ms, "gemm_ms_per_step": gemm_ms / args.steps,
+                       "rows": rows}, f, indent=1)
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_baseline(budget_s=20.0):
+    """Oracle (fp32 restatement of the reference) on the host cores: one dual
+    JointTransformerBlock + one VTSelfAttentionBlock at north-star width on a bounded
+    number of view-frame items; steps/s extrapolated by FLOPs (all cost is per item)."""
+    from oracle import d31, ctsd as octsd
+    from tools import flops as fl
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    D, S, L, items = 1536, 448, 154, 2
+    torch.manual_seed(0)
+    jb = d31.JointTransformerBlock(D, 24, 64, False, "rms_norm", True).eval()
+    vt = octsd.VTSelfAttentionBlock(D, D, 24, 64, "rms_norm").eval()
+    x, c, temb = torch.randn(items, S, D), torch.randn(items, L, D), torch.randn(items, D)
+    xv = torch.randn(items * S // 16, 16, D)
+    f_j = items * ((24 + 8) * S * D * D + 24 * L * D * D + 4 * (S + L) ** 2 * D +
+                   4 * S * S * D + 2 * D * 15 * D)
+    f_v = items * (56 * S * D * D + 4 * 16 * D * S)
+    t_used, reps = 0.0, 0
+    with torch.no_grad():
+        jb(x, c, temb)
+        vt(xv)
+        while t_used < budget_s and reps < 50:
+            t0 = time.perf_counter()
+            jb(x, c, temb)
+            vt(xv)
+            t_used += time.perf_counter() - t0
+            reps += 1
+    tflops = (f_j + f_v) * reps / t_used / 1e12
+    return {"value": tflops / F_STEP_TFLOP, "unit": "steps/s", "cores": cores,
+            "kind": "port", "cpu_tflops_fp32": tflops,
+            "sample": "oracle fp32: 1 dual JointTransformerBlock + 1 VTSelfAttentionBlock, "
+                      "D=1536, %d view-frame items, %d reps in %.1f s; extrapolated by "
+                      "FLOPs to the %.1f TFLOP step" % (items, reps, t_used, F_STEP_TFLOP)}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own semantics (oracle restatement; the reference
+    itself needs diffusers==0.31.0 which is not installable offline) on the host CPU,
+    full-depth north-star model, a bounded sample of the workload per step: 1 frame x
+    6 views without CFG (6 of the 192 view-frame items); steps/s scaled by 192/6."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ctsd as octsd
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = load_config(args.small)
+    B, T, V, C, H, W = cfg["latent_shape"]
+    mcfg = dict(cfg["model"])
+    t0 = time.perf_counter()
+    with torch.device("meta"):
+        model = octsd.DiTCrossviewTemporalConditionModel(**mcfg)
+    model = model.to_empty(device="cpu").eval()
+    pattern = torch.randn(1 << 22, generator=torch.Generator().manual_seed(0)) * 0.02
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1 and name.endswith(".weight"):
+                p.fill_(1.0)
+            elif name.endswith(".bias") or name.endswith("mix_factor"):
+                p.fill_(0.0)
+            else:                                # N(0, 0.02) pattern, tiled (fast init)
+                flat = p.view(-1)
+                n = flat.numel()
+                for s0 in range(0, n, pattern.numel()):
+                    m = min(pattern.numel(), n - s0)
+                    flat[s0:s0 + m] = pattern[:m]
+        pe = model.pos_embed.pos_embed
+        pe.copy_(torch.zeros_like(pe))
+    t_build = time.perf_counter() - t0
+    Ts, items = 1, V
+    cond = synthetic_conditions(cfg, 1, Ts, V, "cpu", torch.float32)
+    sample = torch.randn(1, Ts, V, C, H, W)
+    timestep = torch.full((1, Ts, V), 500.0)
+    times = []
+    with torch.no_grad():
+        for k in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            model(sample, timestep, **cond)
+            dt = time.perf_counter() - t0
+            if k >= args.warmup:
+                times.append(dt)
+    full_items = 2 * B * T * V
+    ms = statistics.mean(times) * 1000.0 * full_items / items
+    line = {
+        "impl": "reference", "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ctsd_35 DFoT 6-view x 16-frame with layout",
+                   "latent_shape": [2 * B, T, V, C, H, W]},
+        "cpu_baseline": {
+            "value": 1000.0 / ms, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": "oracle fp32 full-depth DiT forward incl. ImageAdapter on 1 frame x "
+                      "%d views (no CFG) = %d of %d view-frame items per timed step, "
+                      "scaled x%d; model build %.0f s" % (V, items, full_items,
+                                                          full_items // items, t_build)},
+        "e2e": {"value": 1000.0 / ms, "unit": "steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--small", action="store_true", help="debug-size model/shape")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--profile-dump", default=None,
+                    help="write per-shape GEMM timing of the timed steps to this JSON")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3 and not args.small:
+            args.warmup = 3
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,8 @@ typedef struct dwm_linear_args {
   const float* k_norm_weight; /* [64] */
   int64_t qk_region;          /* D */
   float eps;
+  int qk_norm_regions;        /* regions [0, n) are normalised (0 => default 2: q and k);
+                                 region 0 uses q_norm_weight, region 1 k_norm_weight */
   /* RESID */
   const float* resid;   /* fp32 [*, ldr] or NULL */
   int64_t ldr;
@@ -136,6 +138,17 @@ typedef struct dwm_attention_args {
   int mask_div;
   int n_outer;
   float scale;
+  /* Optional separate key/value source (kv != NULL): keys at column k_col + h*64, values
+   * at v_col + h*64 of `kv`, with their own row formula.  Used when the frame axis is
+   * sharded across GPUs: queries are the local frames, keys/values the all-gathered
+   * frames of every rank (position j = rank*T_local + t_local). */
+  const void* kv;
+  int64_t ld_kv;
+  int64_t k_col, v_col;
+  int64_t kv_group_strides[3];
+  int seq_kv;
+  int inner_kv;
+  int64_t kv_stride_outer, kv_stride_inner;
 } dwm_attention_args;
 
 int dwm_b200_attention(const dwm_attention_args* args, dwm_stream_t stream);

@@ -22,14 +22,19 @@ namespace dwm {
 constexpr int HD = 64;
 
 struct AttnParams {
-  const void* qkv;
-  long long ld;   // row pitch of qkv (elements)
-  int D;          // q at col h*64, k at D + h*64, v at 2D + h*64
+  const void* q;      // queries: row pitch ldq, head h at column h*64
+  long long ldq;
+  const void* kv;     // keys at column kcol0 + h*64, values at vcol0 + h*64
+  long long ldkv;
+  int kcol0, vcol0;
   int heads;
   int groups, G1, G2;
-  long long gs0, gs1, gs2;
-  int seq, inner;
+  long long gs0, gs1, gs2;     // query group strides
+  long long kgs0, kgs1, kgs2;  // key/value group strides
+  int seq, inner;              // queries
   long long so, si;
+  int seq_k, inner_k;          // keys / values
+  long long kso, ksi;
   void* out;
   long long ldo;
   long long ogs0, ogs1, ogs2, oso, osi;
@@ -95,6 +100,9 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
 __device__ __forceinline__ long long tok_row(const AttnParams& p, long long base, int j) {
   return base + static_cast<long long>(j / p.inner) * p.so + static_cast<long long>(j % p.inner) * p.si;
 }
+__device__ __forceinline__ long long key_row(const AttnParams& p, long long base, int j) {
+  return base + static_cast<long long>(j / p.inner_k) * p.kso + static_cast<long long>(j % p.inner_k) * p.ksi;
+}
 
 // NW warps per CTA, 16 query rows per warp, KVT keys per streamed tile.
 template <typename T, int NW, int KVT>
@@ -115,11 +123,13 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const AttnParams p) {
   const int g1 = (g / p.G2) % p.G1;
   const int g0 = g / (p.G2 * p.G1);
   const long long base = g0 * p.gs0 + g1 * p.gs1 + g2 * p.gs2;
+  const long long kbase = g0 * p.kgs0 + g1 * p.kgs1 + g2 * p.kgs2;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const T* qkv = reinterpret_cast<const T*>(p.qkv);
+  const T* qptr = reinterpret_cast<const T*>(p.q);
+  const T* kvptr = reinterpret_cast<const T*>(p.kv);
   const int q0 = qt * QROWS;
 
   // ---- stage Q (gathered rows) ----
@@ -127,23 +137,23 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const AttnParams p) {
     const int r = i >> 3, c = i & 7;
     const int j = q0 + r;
     const bool ok = j < p.seq;
-    const T* src = qkv + (ok ? tok_row(p, base, j) : 0) * p.ld + head * HD + c * 8;
+    const T* src = qptr + (ok ? tok_row(p, base, j) : 0) * p.ldq + head * HD + c * 8;
     cp_async16(sq + tile_off(r, c), src, ok);
   }
   auto load_kv = [&](int buf, int k0) {
     for (int i = tid; i < KVT * 8; i += NT) {
       const int r = i >> 3, c = i & 7;
       const int j = k0 + r;
-      const bool ok = j < p.seq;
-      const T* src = qkv + (ok ? tok_row(p, base, j) : 0) * p.ld + p.D + head * HD + c * 8;
-      cp_async16(sk[buf] + tile_off(r, c), src, ok);
-      cp_async16(sv[buf] + tile_off(r, c), src + p.D, ok);
+      const bool ok = j < p.seq_k;
+      const T* src = kvptr + (ok ? key_row(p, kbase, j) : 0) * p.ldkv + head * HD + c * 8;
+      cp_async16(sk[buf] + tile_off(r, c), src + p.kcol0, ok);
+      cp_async16(sv[buf] + tile_off(r, c), src + p.vcol0, ok);
     }
   };
   load_kv(0, 0);
   cp_async_commit();
 
-  const int n_kv = (p.seq + KVT - 1) / KVT;
+  const int n_kv = (p.seq_k + KVT - 1) / KVT;
   const int gq = lane >> 2;  // fragment row within 8
   const int tq = lane & 3;
 
@@ -206,9 +216,9 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const AttnParams p) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int jk = k0 + nt * 8 + tq * 2 + e;
-        bool ok0 = jk < p.seq, ok1 = ok0;
+        bool ok0 = jk < p.seq_k, ok1 = ok0;
         if (p.mask && ok0) {
-          const int vo = jk / p.inner;
+          const int vo = jk / p.inner_k;
           ok0 = mrow0[vo] != 0;
           ok1 = mrow1[vo] != 0;
         }
@@ -305,10 +315,11 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const AttnParams p) {
 
 template <typename T>
 static int launch_attn(const AttnParams& p, cudaStream_t s) {
-  if (p.seq <= 16) {
+  const int smax = p.seq > p.seq_k ? p.seq : p.seq_k;
+  if (smax <= 16) {
     const long long blocks = static_cast<long long>(p.groups) * p.heads;
     attn_kernel<T, 1, 16><<<static_cast<unsigned>(blocks), 32, 0, s>>>(p);
-  } else if (p.seq <= 32) {
+  } else if (smax <= 32) {
     const long long blocks = static_cast<long long>(p.groups) * p.heads;
     attn_kernel<T, 2, 32><<<static_cast<unsigned>(blocks), 64, 0, s>>>(p);
   } else {
@@ -338,10 +349,24 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
     DWM_REQUIRE(a->out2 && a->ldo2 % 8 == 0 && a->split < a->seq, "dwm_b200_attention: bad split/out2");
   if (a->mask) DWM_REQUIRE(a->mask_div > 0 && a->n_outer > 0, "dwm_b200_attention: mask needs mask_div, n_outer");
   const long long groups = static_cast<long long>(a->group_dims[0]) * a->group_dims[1] * a->group_dims[2];
-  const long long q_tiles = a->seq <= 32 ? 1 : (a->seq + 63) / 64;
+  if (a->kv)
+    DWM_REQUIRE(a->ld_kv % 8 == 0 && a->k_col % 8 == 0 && a->v_col % 8 == 0 && a->seq_kv > 0 && a->inner_kv > 0 &&
+                    (reinterpret_cast<uintptr_t>(a->kv) & 15) == 0,
+                "dwm_b200_attention: bad separate kv description");
+  const int seq_max = (a->kv && a->seq_kv > a->seq) ? a->seq_kv : a->seq;
+  const long long q_tiles = seq_max <= 32 ? 1 : (a->seq + 63) / 64;
   DWM_REQUIRE(groups * a->heads * q_tiles < (1ll << 31), "dwm_b200_attention: grid too large");
   AttnParams p;
-  p.qkv = a->qkv; p.ld = a->ld; p.D = static_cast<int>(a->D); p.heads = a->heads;
+  p.q = a->qkv; p.ldq = a->ld; p.heads = a->heads;
+  if (a->kv) {
+    p.kv = a->kv; p.ldkv = a->ld_kv; p.kcol0 = static_cast<int>(a->k_col); p.vcol0 = static_cast<int>(a->v_col);
+    p.kgs0 = a->kv_group_strides[0]; p.kgs1 = a->kv_group_strides[1]; p.kgs2 = a->kv_group_strides[2];
+    p.seq_k = a->seq_kv; p.inner_k = a->inner_kv; p.kso = a->kv_stride_outer; p.ksi = a->kv_stride_inner;
+  } else {
+    p.kv = a->qkv; p.ldkv = a->ld; p.kcol0 = static_cast<int>(a->D); p.vcol0 = static_cast<int>(2 * a->D);
+    p.kgs0 = a->group_strides[0]; p.kgs1 = a->group_strides[1]; p.kgs2 = a->group_strides[2];
+    p.seq_k = a->seq; p.inner_k = a->inner; p.kso = a->stride_outer; p.ksi = a->stride_inner;
+  }
   p.groups = static_cast<int>(groups); p.G1 = static_cast<int>(a->group_dims[1]); p.G2 = static_cast<int>(a->group_dims[2]);
   p.gs0 = a->group_strides[0]; p.gs1 = a->group_strides[1]; p.gs2 = a->group_strides[2];
   p.seq = a->seq; p.inner = a->inner; p.so = a->stride_outer; p.si = a->stride_inner;

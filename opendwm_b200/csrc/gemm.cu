@@ -42,6 +42,7 @@ struct EpiParams {
   const float* kw;
   long long qk_region;
   float eps;
+  int norm_regions;
   const float* resid;
   long long ldr, resid_row_mod;
   const float* gate;
@@ -250,7 +251,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
         }
       }
       const int region = n0 / static_cast<int>(p.qk_region);
-      if (region < 2) {
+      if (region < p.norm_regions) {
         const float* w = region == 0 ? p.qw : p.kw;
         float ss = 0.f;
 #pragma unroll
@@ -419,6 +420,7 @@ static int launch_gemm(const dwm_linear_args* a, cudaStream_t stream) {
   p.kw = a->k_norm_weight;
   p.qk_region = a->qk_region;
   p.eps = a->eps;
+  p.norm_regions = a->qk_norm_regions > 0 ? a->qk_norm_regions : 2;
   p.resid = a->resid;
   p.ldr = a->ldr;
   p.resid_row_mod = a->resid_row_mod;
@@ -483,7 +485,7 @@ extern "C" int dwm_b200_linear(const dwm_linear_args* a, dwm_stream_t stream) {
     DWM_REQUIRE(a->N % 256 == 0, "dwm_b200_linear: GEGLU needs N %% 256 == 0 (packed weight)");
   if (a->epilogue == DWM_EPI_QKNORM) {
     DWM_REQUIRE(a->N % 64 == 0 && a->qk_region > 0 && a->qk_region % 64 == 0 && a->q_norm_weight &&
-                    a->k_norm_weight,
+                    (a->k_norm_weight || a->qk_norm_regions == 1),
                 "dwm_b200_linear: QKNORM needs head_dim 64 regions and both norm weights");
   }
   if (a->epilogue == DWM_EPI_RESID && a->blend_x)

@@ -29,7 +29,7 @@ class LinearArgs(ctypes.Structure):
         ("rows_per_item", _i64), ("out_item_stride", _i64),
         ("out_row_offset", _i64),
         ("q_norm_weight", _p), ("k_norm_weight", _p), ("qk_region", _i64),
-        ("eps", ctypes.c_float),
+        ("eps", ctypes.c_float), ("qk_norm_regions", ctypes.c_int),
         ("resid", _p), ("ldr", _i64), ("resid_row_mod", _i64),
         ("gate", _p), ("gate_ld", _i64),
         ("blend_x", _p), ("ldx", _i64),
@@ -51,6 +51,10 @@ class AttentionArgs(ctypes.Structure):
         ("split", ctypes.c_int), ("out2", _p), ("ldo2", _i64),
         ("mask", _p), ("mask_div", ctypes.c_int), ("n_outer", ctypes.c_int),
         ("scale", ctypes.c_float),
+        ("kv", _p), ("ld_kv", _i64), ("k_col", _i64), ("v_col", _i64),
+        ("kv_group_strides", _i64 * 3),
+        ("seq_kv", ctypes.c_int), ("inner_kv", ctypes.c_int),
+        ("kv_stride_outer", _i64), ("kv_stride_inner", _i64),
     ]
 
 

@@ -20,7 +20,31 @@ def _ptr(t):
 
 
 def _stream():
+    if _prof is not None:
+        _prof["launches"] += 1
     return torch.cuda.current_stream().cuda_stream
+
+
+_prof = None
+
+
+def profile_begin():
+    """Starts counting kernel launches and timing every dwm_b200_linear launch with a
+    CUDA event pair on the launching stream (used by bench.py's roofline figure)."""
+    global _prof
+    _prof = {"launches": 0, "events": []}
+
+
+def profile_end():
+    """Stops profiling; call after a stream synchronize.  Returns
+    {"launches": n, "linear": [{"ms", "flops", "shape", "epilogue"}, ...]}."""
+    global _prof
+    p, _prof = _prof, None
+    out = {"launches": p["launches"], "linear": []}
+    for e0, e1, flops, shape, epi in p["events"]:
+        out["linear"].append({"ms": e0.elapsed_time(e1), "flops": flops,
+                              "shape": shape, "epilogue": epi})
+    return out
 
 
 def _f32(t, name):
@@ -41,7 +65,7 @@ def _rows2d(t, name):
 def linear(a, w, bias=None, *, epilogue=_l.EPI_STORE, act=_l.ACT_NONE,
            out=None, rows_per_item=0, out_item_stride=0, out_row_offset=0,
            q_norm_weight=None, k_norm_weight=None, qk_region=0, eps=1e-6,
-           resid=None, resid_row_mod=0, gate=None, blend_x=None, alpha=None,
+           qk_norm_regions=0, resid=None, resid_row_mod=0, gate=None, blend_x=None, alpha=None,
            rows_per_batch=0):
     """out = epilogue(a @ w.T).  a [M,K], w [N,K] 16-bit; see include/dwm_b200.h."""
     _rows2d(a, "a")
@@ -81,6 +105,7 @@ def linear(a, w, bias=None, *, epilogue=_l.EPI_STORE, act=_l.ACT_NONE,
     args.k_norm_weight = _ptr(_f32(k_norm_weight, "k_norm_weight"))
     args.qk_region = qk_region
     args.eps = eps
+    args.qk_norm_regions = qk_norm_regions
     if resid is not None:
         _rows2d(_f32(resid, "resid"), "resid")
         args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
@@ -93,7 +118,15 @@ def linear(a, w, bias=None, *, epilogue=_l.EPI_STORE, act=_l.ACT_NONE,
         args.blend_x, args.ldx = blend_x.data_ptr(), blend_x.stride(0)
     args.alpha = _ptr(_f32(alpha, "alpha"))
     args.rows_per_batch = rows_per_batch
-    rc = _l.load().dwm_b200_linear(ctypes.byref(args), _stream())
+    if _prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _l.load().dwm_b200_linear(ctypes.byref(args), _stream())
+        e1.record()
+        _prof["events"].append((e0, e1, 2.0 * M * N * K, (M, N, K), epilogue))
+    else:
+        rc = _l.load().dwm_b200_linear(ctypes.byref(args), _stream())
     _l.check(rc, "dwm_b200_linear")
     return out
 
@@ -126,9 +159,11 @@ def _code(dtype):
 def attention(qkv, out, *, D, heads, group_dims, group_strides, seq, inner=None,
               stride_outer=0, stride_inner=1, out_group_strides=None,
               out_stride_outer=None, out_stride_inner=None, split=0, out2=None,
-              mask=None, mask_div=1, scale=None):
-    """Gathered multi-head attention over the fused q|k|v buffer; see
-    dwm_attention_args in include/dwm_b200.h."""
+              mask=None, mask_div=1, scale=None, kv=None, k_col=0, v_col=0,
+              kv_group_strides=None, seq_kv=None, inner_kv=None,
+              kv_stride_outer=0, kv_stride_inner=1):
+    """Gathered multi-head attention over the fused q|k|v buffer (or a separate
+    key/value buffer `kv`); see dwm_attention_args in include/dwm_b200.h."""
     _rows2d(qkv, "qkv")
     _rows2d(out, "out")
     if not qkv.is_cuda:
@@ -159,6 +194,17 @@ def attention(qkv, out, *, D, heads, group_dims, group_strides, seq, inner=None,
             raise TypeError("mask must be a contiguous uint8 [B, n, n] tensor")
         a.mask, a.mask_div, a.n_outer = mask.data_ptr(), mask_div, mask.shape[-1]
     a.scale = (D // heads) ** -0.5 if scale is None else scale
+    if kv is not None:
+        _rows2d(kv, "kv")
+        if kv.dtype != qkv.dtype:
+            raise TypeError("kv dtype differs from q dtype")
+        a.kv, a.ld_kv, a.k_col, a.v_col = kv.data_ptr(), kv.stride(0), k_col, v_col
+        kgs = list(kv_group_strides) + [0] * (3 - len(kv_group_strides))
+        for i in range(3):
+            a.kv_group_strides[i] = kgs[i]
+        a.seq_kv = seq if seq_kv is None else seq_kv
+        a.inner_kv = a.seq_kv if inner_kv is None else inner_kv
+        a.kv_stride_outer, a.kv_stride_inner = kv_stride_outer, kv_stride_inner
     _l.check(_l.load().dwm_b200_attention(ctypes.byref(a), _stream()),
              "dwm_b200_attention")
     return out

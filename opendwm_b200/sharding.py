@@ -1,0 +1,94 @@
+"""View-frame sharding plan of the denoise step across GPUs.
+
+The CFG-doubled 6 x T view-frame grid is split first over the two classifier-free-
+guidance branches (they never interact inside the forward; only the final CFG combine
+needs the partner's prediction) and then over the frame axis T.  Cross-view attention
+couples the views of ONE frame, so it stays rank-local; temporal attention couples the
+frames of one view, so each temporal block all-gathers its post-norm K,V over the
+frame group (NCCL over NVLink).  Everything else is per view-frame item.
+
+One process per GPU; collectives go through torch.distributed (nccl on GPUs, gloo in
+the CPU tests of this module's index arithmetic).
+"""
+import torch
+import torch.distributed as dist
+
+FRAME_KEYS = ("encoder_hidden_states", "pooled_projections",
+              "condition_image_tensor", "added_time_ids", "camera_intrinsics",
+              "camera_transforms")
+
+
+class ShardPlan:
+    def __init__(self, world: int, rank: int, frames: int, cfg: bool = True,
+                 make_groups: bool = True):
+        self.world, self.rank, self.T = world, rank, frames
+        self.cfg_ways = 2 if (cfg and world >= 2) else 1
+        if world % self.cfg_ways:
+            raise ValueError("world size {} not divisible by {}".format(
+                world, self.cfg_ways))
+        self.t_ways = world // self.cfg_ways
+        if frames % self.t_ways:
+            raise ValueError("{} frames not divisible over {} frame shards".format(
+                frames, self.t_ways))
+        self.cfg_rank, self.t_rank = rank // self.t_ways, rank % self.t_ways
+        self.T_loc = frames // self.t_ways
+        self.t_offset = self.t_rank * self.T_loc
+        self.t_group = self.cfg_group = None
+        if make_groups and world > 1:
+            # every rank must take part in creating every group
+            for c in range(self.cfg_ways):
+                ranks = [c * self.t_ways + t for t in range(self.t_ways)]
+                g = dist.new_group(ranks) if self.t_ways > 1 else None
+                if c == self.cfg_rank:
+                    self.t_group = g
+            for t in range(self.t_ways):
+                ranks = [c * self.t_ways + t for c in range(self.cfg_ways)]
+                g = dist.new_group(ranks) if self.cfg_ways > 1 else None
+                if t == self.t_rank:
+                    self.cfg_group = g
+
+    @property
+    def parallelism(self):
+        return "cfg{}xframes{}".format(self.cfg_ways, self.t_ways)
+
+    def frame_slice(self):
+        return slice(self.t_offset, self.t_offset + self.T_loc)
+
+    def local_conditions(self, conditions: dict, cfg_doubled: bool):
+        """Slices CFG-doubled, full-length conditions to this rank's branch / frames."""
+        out = {}
+        for k, v in conditions.items():
+            if v is None:
+                out[k] = None
+                continue
+            if cfg_doubled and self.cfg_ways == 2:
+                half = v.shape[0] // 2
+                v = v[self.cfg_rank * half:(self.cfg_rank + 1) * half]
+            if k in FRAME_KEYS and v.dim() > 1 and v.shape[1] == self.T:
+                v = v[:, self.frame_slice()]
+            out[k] = v.contiguous()
+        return out
+
+    def local_latents(self, latents):
+        return latents[:, self.frame_slice()].contiguous()
+
+    # ---- collectives -------------------------------------------------------------------
+    def gather_frames_kv(self, kv_local: torch.Tensor, kv_all: torch.Tensor,
+                         async_op: bool = False):
+        """kv_all[r] = kv_local of frame-shard r.  Key position j = r*T_loc + t_loc of a
+        (batch, view, token) group then lives at row
+        r*rows_local + b*(T_loc*V*S) + t_loc*(V*S) + v*S + s of kv_all.view(-1, 2D)."""
+        return dist.all_gather_into_tensor(kv_all, kv_local, group=self.t_group,
+                                           async_op=async_op)
+
+    def gather_cfg_tokens(self, tokens: torch.Tensor, out: torch.Tensor):
+        """out = [uncond tokens ; cond tokens] on both ranks of the CFG pair."""
+        return dist.all_gather_into_tensor(out, tokens, group=self.cfg_group)
+
+    def gather_latents(self, latents_local):
+        """Full [B, T, V, ...] latents from the frame shards (end of window / tests)."""
+        if self.t_ways == 1:
+            return latents_local
+        parts = [torch.empty_like(latents_local) for _ in range(self.t_ways)]
+        dist.all_gather(parts, latents_local.contiguous(), group=self.t_group)
+        return torch.cat(parts, dim=1)

@@ -155,6 +155,10 @@ class VTSelfAttentionBlock(torch.nn.Module):
             [at.to_q.weight, at.to_k.weight, at.to_v.weight]))
         p["qkv_b"] = None if at.to_q.bias is None else f32(torch.cat(
             [at.to_q.bias, at.to_k.bias, at.to_v.bias]))
+        D = self.dim
+        p["q_w"], p["kv_w"] = p["qkv_w"][:D], p["qkv_w"][D:]   # row slices (views)
+        p["q_b"] = None if p["qkv_b"] is None else p["qkv_b"][:D]
+        p["kv_b"] = None if p["qkv_b"] is None else p["qkv_b"][D:]
         p["qk_norm"] = at.qk_norm == "rms_norm"
         if p["qk_norm"]:
             p["nq"], p["nk"] = f32(at.norm_q.weight), f32(at.norm_k.weight)
@@ -166,10 +170,13 @@ class VTSelfAttentionBlock(torch.nn.Module):
         self._packed = p
         return p
 
-    def run(self, p, x, emb, rows_per_item, ws, attend, alpha, rows_per_batch):
+    def run(self, p, x, emb, rows_per_item, ws, attend, alpha, rows_per_batch,
+            qkv_attend=None):
         """x: fp32 residual stream [M, D] (updated in place with the blended result);
         emb: fp32 [items, D] added before the block (view / frame index embedding);
-        attend(qkv, out): launches the regrouped attention; alpha: fp32 [B]."""
+        attend(qkv, out): launches the regrouped attention; alpha: fp32 [B];
+        qkv_attend(p, a16, out): optional replacement of projection + attention
+        (frame-sharded temporal attention with a K,V all-gather)."""
         D = self.dim
         y, a16, g16, qkv, o16 = ws["y"], ws["a16"], ws["g16"], ws["qkv_s"], ws["o16"]
         _ops.layernorm(x, a16, weight=p["norm_in_w"], bias=p["norm_in_b"],
@@ -181,13 +188,16 @@ class VTSelfAttentionBlock(torch.nn.Module):
                     resid=y, out=y)
         _ops.layernorm(y, a16, weight=p["norm1_w"], bias=p["norm1_b"],
                        eps=p["norm1_eps"])
-        if p["qk_norm"]:
-            _ops.linear(a16, p["qkv_w"], p["qkv_b"], epilogue=_lib.EPI_QKNORM,
-                        out=qkv, q_norm_weight=p["nq"], k_norm_weight=p["nk"],
-                        qk_region=D, eps=self.attn1.eps)
+        if qkv_attend is not None:
+            qkv_attend(p, a16, o16)
         else:
-            _ops.linear(a16, p["qkv_w"], p["qkv_b"], out=qkv)
-        attend(qkv, o16)
+            if p["qk_norm"]:
+                _ops.linear(a16, p["qkv_w"], p["qkv_b"], epilogue=_lib.EPI_QKNORM,
+                            out=qkv, q_norm_weight=p["nq"], k_norm_weight=p["nk"],
+                            qk_region=D, eps=self.attn1.eps)
+            else:
+                _ops.linear(a16, p["qkv_w"], p["qkv_b"], out=qkv)
+            attend(qkv, o16)
         _ops.linear(o16, p["out_w"], p["out_b"], epilogue=_lib.EPI_RESID,
                     resid=y, out=y)
         _ops.layernorm(y, a16, weight=p["norm3_w"], bias=p["norm3_b"],

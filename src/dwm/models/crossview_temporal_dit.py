@@ -242,7 +242,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         self._ws = {}            # workspaces keyed by shape
         self._cond_key = None
         self._cond = None
-        self.shard = None        # (rank, world, process_group) frame-axis sharding
+        self.shard = None        # opendwm_b200.sharding.ShardPlan (frame-axis sharding)
 
     # -- nn.Module plumbing the pipeline relies on ---------------------------------
     def enable_gradient_checkpointing(self):
@@ -526,6 +526,47 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                                seq=T, inner=1, stride_outer=V * S, stride_inner=0)
         return attend
 
+    def _temporal_qkv_attend_sharded(self, B, T_loc, V, Hp, Wp, ws):
+        """Frame-sharded temporal attention: K,V of the local frames are projected
+        (+RMSNorm) into a contiguous slab, all-gathered over the frame group while the
+        Q projection runs, then every local query frame attends to all T frames."""
+        plan = self.shard
+        if self.temporal_attention_type in ("full", "rowwise"):
+            raise NotImplementedError(
+                "frame sharding is implemented for pointwise temporal attention")
+        S, D, heads = Hp * Wp, self.inner_dim, self.heads
+        rows = B * T_loc * V * S
+        dt, dev = ws["a16"].dtype, ws["a16"].device
+        if "kv_loc" not in ws:
+            ws["kv_loc"] = torch.empty(rows, 2 * D, device=dev, dtype=dt)
+            ws["kv_all"] = torch.empty(plan.t_ways * rows, 2 * D, device=dev, dtype=dt)
+            ws["q_loc"] = torch.empty(rows, D, device=dev, dtype=dt)
+        kv_loc, kv_all, q_loc = ws["kv_loc"], ws["kv_all"], ws["q_loc"]
+        eps = 1e-5
+
+        def qkv_attend(p, a16, out):
+            if p["qk_norm"]:
+                _ops.linear(a16, p["kv_w"], p["kv_b"], epilogue=_lib.EPI_QKNORM,
+                            out=kv_loc, q_norm_weight=p["nk"], qk_region=D,
+                            qk_norm_regions=1, eps=eps)
+            else:
+                _ops.linear(a16, p["kv_w"], p["kv_b"], out=kv_loc)
+            work = plan.gather_frames_kv(kv_loc, kv_all, async_op=True)
+            if p["qk_norm"]:
+                _ops.linear(a16, p["q_w"], p["q_b"], epilogue=_lib.EPI_QKNORM,
+                            out=q_loc, q_norm_weight=p["nq"], qk_region=D,
+                            qk_norm_regions=1, eps=eps)
+            else:
+                _ops.linear(a16, p["q_w"], p["q_b"], out=q_loc)
+            work.wait()
+            _ops.attention(
+                q_loc, out, D=D, heads=heads, group_dims=[B, V * S],
+                group_strides=[T_loc * V * S, 1], seq=T_loc, inner=1,
+                stride_outer=V * S, stride_inner=0, kv=kv_all, k_col=0, v_col=D,
+                kv_group_strides=[T_loc * V * S, 1], seq_kv=plan.T,
+                inner_kv=T_loc, kv_stride_outer=rows, kv_stride_inner=V * S)
+        return qkv_attend
+
     # -- one JointTransformerBlock ----------------------------------------------------------
     def _joint_block(self, b, ws, N, S, L, residual):
         D, heads = self.inner_dim, self.heads
@@ -649,6 +690,10 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
             if self.enable_crossview else None
         tp_attend = self._temporal_attend(B, T, V, Hp, Wp) \
             if self.enable_temporal else None
+        tp_sharded = None
+        if self.enable_temporal and self.shard is not None and \
+                self.shard.t_ways > 1:
+            tp_sharded = self._temporal_qkv_attend_sharded(B, T, V, Hp, Wp, ws)
         for i, b in enumerate(pk["blocks"]):
             res = residuals.pop(0) if residuals else None
             self._joint_block(b, ws, N, S, L, res)
@@ -656,7 +701,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                 k = self.temporal_block_layers.index(i)
                 self.temporal_transformer_blocks[k].run(
                     pk["tp"][k], ws["x"], cd["temb_tab"][k], S, ws, tp_attend,
-                    cd["t_alpha"][k], T * V * S)
+                    cd["t_alpha"][k], T * V * S, qkv_attend=tp_sharded)
             if self.enable_crossview and i in self.crossview_block_layers:
                 k = self.crossview_block_layers.index(i)
                 self.crossview_transformer_blocks[k].run(

@@ -1,0 +1,485 @@
+"""CTSD inference pipelines — mirror of the denoising part of reference
+src/dwm/pipelines/ctsd.py: `CrossviewTemporalSD` (ctor :844-1012, condition building
+:84-464) and `StreamingCrossviewTemporalSD` (diffusion-forcing FIFO :2010-2277).
+
+Scope: the denoise loop, its integer timestep-index schedule, CFG
+batching, the model call and the scheduler update run on the B200-native kernels
+(`model.forward_tokens` + one fused CFG / un-patchify / per-frame-Euler / masked-update
+kernel per step, no host synchronisation inside the loop).  Training, evaluation,
+preview dumping and the text encoders are outside the hot path; text conditions are
+taken pre-encoded from the batch (`text_embeddings` / `pooled_text_embeddings` and
+their `uncond_*` twins for classifier-free guidance) because the CLIP/T5 checkpoints
+are not part of this implementation.  VAE decode happens when a `vae` object with
+the diffusers decode interface is supplied (`common_config["vae_instance"]`);
+otherwise the exiting latents are returned.
+"""
+import os
+
+import torch
+
+import dwm.common
+import dwm.functional
+from dwm import _compat
+from dwm.schedulers import temporal_independent as _ti
+from opendwm_b200 import ops as _ops
+
+
+class CrossviewTemporalSD:
+
+    @staticmethod
+    def load_state(path: str):
+        """reference :29-36."""
+        if path.endswith(".safetensors"):
+            import safetensors.torch
+            return safetensors.torch.load_file(path, device="cpu")
+        return torch.load(path, map_location="cpu", weights_only=True)
+
+    @staticmethod
+    def get_camera_transform_ids(batch, common_config):
+        """reference :84-95."""
+        return torch.cat([
+            batch["camera_intrinsics"].flatten(-2, -1)[
+                ..., common_config["camera_intrinsic_embedding_indices"]
+            ] / batch["image_size"][
+                ..., common_config["camera_intrinsic_denom_embedding_indices"]
+            ],
+            batch["camera_transforms"].flatten(-2, -1)[
+                ..., common_config["camera_transform_embedding_indices"]
+            ]
+        ], -1)
+
+    @staticmethod
+    def get_action_ids(batch, common_config: dict, action_condition_mask=None,
+                       streaming_mode: bool = False, prev_ego_transforms=None):
+        """Speed (km/h) and steering from consecutive ego poses; -1000 marks the
+        unconditional case (reference :97-156)."""
+        if streaming_mode:
+            assert batch["ego_transforms"].shape[1] == 1
+            ego_transforms = torch.cat([
+                batch["ego_transforms"] if prev_ego_transforms is None
+                else prev_ego_transforms,
+                batch["ego_transforms"]], dim=1)
+        else:
+            ego_transforms = batch["ego_transforms"]
+        current_pose = ego_transforms[
+            :, :, common_config["camera_ego_sensor_indices"]]
+        uncondition_pose = torch.eye(4).view(1, 1, 1, 4, 4)
+        is_conditioned = (current_pose - uncondition_pose)\
+            .sum((1, 2, 3, 4)).abs() > 1e-3
+        if action_condition_mask is not None:
+            is_conditioned = torch.logical_and(
+                is_conditioned, action_condition_mask)
+        relative_pose = torch.linalg.solve(
+            current_pose[:, :-1], current_pose[:, 1:])
+        relative_pose = torch.cat([relative_pose[:, :1], relative_pose], 1)
+        moving_distance = torch.norm(
+            relative_pose[..., :3, 3], dim=-1, keepdim=True)
+        speed = 3.6 * moving_distance * batch["fps"].view(-1, 1, 1, 1)
+        rotation_angles = torch.atan2(
+            relative_pose[..., 1, 0:1] - relative_pose[..., 0, 1:2],
+            relative_pose[..., 0, 0:1] + relative_pose[..., 1, 1:2])
+        wheel_base, steering_ratio = 2.7, 14
+        steering = torch.where(
+            torch.abs(moving_distance) > 0.01,
+            rotation_angles / moving_distance * wheel_base * steering_ratio,
+            -1000.0 * torch.ones_like(rotation_angles))
+        action_ids = torch.cat([speed, steering], -1)
+        action_ids = torch.where(
+            is_conditioned.view(-1, 1, 1, 1), action_ids,
+            -1000.0 * torch.ones_like(action_ids))
+        if streaming_mode:
+            action_ids = action_ids.chunk(2, dim=1)[-1]
+        return action_ids
+
+    @staticmethod
+    def get_conditions(model, text_encoder, tokenizer, common_config: dict,
+                       latent_shape, batch: dict, device, dtype,
+                       text_condition_mask=None, _3dbox_condition_mask=None,
+                       hdmap_condition_mask=None, action_condition_mask=None,
+                       explicit_view_modeling_mask=None,
+                       streaming_mode: bool = False, prev_ego_transforms=None,
+                       do_classifier_free_guidance: bool = False,
+                       latents_shape=None):
+        """Model kwargs from a data batch (reference :158-464).  `text_encoder` is
+        only a flag here: when not None the pre-encoded `text_embeddings`
+        [B,T,V,L,C] / `pooled_text_embeddings` [B,T,V,P] of the batch are used
+        (uncond half = `uncond_*` entries, or zeros when absent)."""
+        batch_size, _, view_count = latent_shape[:3]
+        sequence_length = batch["pts"].shape[1]
+        if do_classifier_free_guidance:
+            batch_size *= 2
+        if common_config.get("explicit_view_modeling", False):
+            raise NotImplementedError(
+                "explicit_view_modeling (UniMLVG) is outside the CTSD hot path")
+
+        encoder_hidden_states = pooled = None
+        if text_encoder is not None and "text_embeddings" in batch:
+            te = batch["text_embeddings"].to(device=device, dtype=dtype)
+            pe = batch["pooled_text_embeddings"].to(device=device, dtype=dtype)
+            if do_classifier_free_guidance:
+                ute = batch.get("uncond_text_embeddings", torch.zeros_like(te))\
+                    .to(device=device, dtype=dtype)
+                upe = batch.get("uncond_pooled_text_embeddings",
+                                torch.zeros_like(pe)).to(device=device, dtype=dtype)
+                te, pe = torch.cat([ute, te]), torch.cat([upe, pe])
+            encoder_hidden_states, pooled = te, pe
+
+        condition_on_all_frames = common_config.get(
+            "condition_on_all_frames", False)
+        color = common_config.get("uncondition_image_color", 0)
+        condition_image_list = []
+        for key, mask in (("3dbox_images", _3dbox_condition_mask),
+                          ("hdmap_images", hdmap_condition_mask)):
+            if key not in batch:
+                continue
+            img = batch[key].to(device) if condition_on_all_frames \
+                else batch[key][:, :1].to(device)
+            if mask is not None:
+                img = img.clone()
+                img[mask.logical_not().to(device)] = color
+            if do_classifier_free_guidance:
+                img = torch.cat([torch.ones_like(img) * color, img])
+            condition_image_list.append(img)
+        condition_image_tensor = torch.cat(condition_image_list, -3) \
+            if condition_image_list else None
+
+        added_time_ids = None
+        kind = common_config.get("added_time_ids")
+        if kind in ("fps_camera_transforms", "fps_camera_transforms_action"):
+            parts = [
+                batch["fps"].view(-1, 1, 1, 1)
+                .repeat(1, sequence_length, view_count, 1),
+                CrossviewTemporalSD.get_camera_transform_ids(batch, common_config)]
+            if kind == "fps_camera_transforms_action":
+                parts.append(CrossviewTemporalSD.get_action_ids(
+                    batch, common_config, action_condition_mask,
+                    streaming_mode, prev_ego_transforms))
+            added_time_ids = torch.cat(parts, -1)
+            if do_classifier_free_guidance:
+                if kind == "fps_camera_transforms_action":
+                    uncond = torch.cat([
+                        added_time_ids[..., :-2],
+                        -1000 * torch.ones_like(added_time_ids[..., -2:])], -1)
+                else:
+                    uncond = added_time_ids
+                added_time_ids = torch.cat([uncond, added_time_ids], 0)
+            added_time_ids = added_time_ids.to(device)
+
+        has_depth_input = "camera_intrinsics" in batch and \
+            "camera_transforms" in batch
+        rep = (lambda t: torch.cat([t, t])) if do_classifier_free_guidance \
+            else (lambda t: t)
+        result = {
+            "encoder_hidden_states": encoder_hidden_states,
+            "condition_image_tensor": condition_image_tensor,
+            "disable_crossview": torch.tensor(
+                [common_config.get("disable_crossview", False)],
+                device=device).repeat(batch_size),
+            "disable_temporal": torch.tensor(
+                [common_config.get("disable_temporal", False)],
+                device=device).repeat(batch_size),
+            "crossview_attention_mask":
+                rep(batch["crossview_mask"]).to(device)
+                if "crossview_mask" in batch else None,
+            "camera_intrinsics": rep(batch["camera_intrinsics"].to(device))
+                if has_depth_input else None,
+            "camera_transforms": rep(batch["camera_transforms"].to(device))
+                if has_depth_input else None,
+            "camera_intrinsics_norm": None,
+            "camera2referego": None,
+            "added_time_ids": added_time_ids,
+        }
+        if isinstance(model, _compat.SD3Transformer2DModelMarker) and \
+                text_encoder is not None:
+            result["pooled_projections"] = pooled
+
+        if latents_shape is not None and latents_shape[1] != sequence_length:
+            pre = 1 if sequence_length % 2 == 1 else 0
+            stride = (sequence_length - pre) // (latents_shape[1] - pre)
+            for k in result:
+                if result[k] is not None and result[k].ndim > 1 and \
+                        result[k].shape[1] == sequence_length:
+                    result[k] = torch.cat(
+                        [result[k][:, :pre], result[k][:, pre::stride]], dim=1)
+        return result
+
+    def __init__(self, output_path, config: dict, device, common_config: dict,
+                 training_config: dict, inference_config: dict,
+                 pretrained_model_name_or_path: str, model, model_dtype=None,
+                 model_checkpoint_path=None, model_load_state_args: dict = {},
+                 metrics: dict = {}, resume_from=None):
+        self.should_save = not torch.distributed.is_initialized() or \
+            torch.distributed.get_rank() == 0
+        self.config = config
+        self.device = torch.device(device)
+        self.common_config = common_config
+        self.training_config = training_config
+        self.inference_config = inference_config
+        self.output_path = output_path
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "dwm.pipelines.ctsd runs on CUDA (sm_100a) only; there is no CPU "
+                "fallback")
+
+        self.generator = torch.Generator()
+        if "generator_seed" in self.config:
+            self.generator.manual_seed(self.config["generator_seed"])
+        else:
+            self.generator.seed()
+
+        self.model_dtype = model_dtype or torch.float32
+        self.model_wrapper = self.model = model.to(dtype=self.model_dtype)
+        self.model.enable_gradient_checkpointing()
+        self.model.to(self.device)
+
+        # text encoders are not part of this implementation: a truthy marker keeps
+        # get_conditions on the "text provided" path when the batch is pre-encoded
+        self.text_encoders = self.tokenizers = "pre-encoded"
+        self.vae = common_config.get("vae_instance")
+        self.is_temporal_vae = bool(common_config.get("vae_is_temporal", False))
+
+        if not isinstance(self.model, _compat.SD3Transformer2DModelMarker):
+            raise NotImplementedError(
+                "only the SD-3.x DiT model family is implemented in this round")
+        test_scheduler_type = dwm.common.get_class(self.inference_config.get(
+            "scheduler",
+            "dwm.schedulers.temporal_independent.FlowMatchEulerDiscreteScheduler"))
+        sched_dir = None if pretrained_model_name_or_path is None else \
+            os.path.join(pretrained_model_name_or_path, "scheduler")
+        if sched_dir is not None and os.path.exists(
+                os.path.join(sched_dir, "scheduler_config.json")):
+            self.test_scheduler = test_scheduler_type.from_pretrained(
+                pretrained_model_name_or_path, subfolder="scheduler")
+        else:
+            # stable-diffusion-3.5-medium scheduler/scheduler_config.json values
+            self.test_scheduler = test_scheduler_type(
+                num_train_timesteps=1000, shift=3.0)
+
+        if resume_from is not None:
+            self.model.load_state_dict(CrossviewTemporalSD.load_state(
+                os.path.join(output_path, "checkpoints",
+                             "{}.pth".format(resume_from))))
+        elif model_checkpoint_path is not None:
+            state_dict = CrossviewTemporalSD.load_state(model_checkpoint_path)
+            missing_keys, unexpected_keys = self.model.load_state_dict(
+                state_dict, **model_load_state_args)
+            if self.should_save and \
+                    self.common_config.get("print_load_state_info", False):
+                print(f"missing keys: {missing_keys}")
+                print(f"unexpected keys: {unexpected_keys}")
+        self.metrics = metrics
+        self._step_cache = {}
+        # optional opendwm_b200.sharding.ShardPlan: this rank then owns one CFG branch /
+        # a slice of the frames and `denoise_step` works on the local latents
+        self.sharding = None
+
+    # -- the fused denoising step ----------------------------------------------------------
+    def _df_step_tensors(self, i, T, spi, take_time, B, V):
+        """Device-resident index tensors of one diffusion-forcing step, cached per
+        (i, take_time): the reference rebuilds them from Python lists every step
+        (:2048-2055, :2083-2088)."""
+        key = (i, T, spi, take_time, B, V, self.test_scheduler.num_inference_steps)
+        hit = self._step_cache.get(key)
+        if hit is None:
+            idx = torch.tensor(
+                _ti.df_timestep_indices(i, T, spi, take_time),
+                dtype=torch.int32, device=self.device)\
+                .view(1, T, 1).repeat(B, 1, V).contiguous()
+            timesteps = self.test_scheduler.timesteps.to(self.device)[idx.long()]
+            in_range = torch.tensor(
+                _ti.df_in_schedule_range(i, T, spi), device=self.device)\
+                .to(torch.uint8).contiguous()
+            hit = (idx, timesteps.float().contiguous(), in_range)
+            self._step_cache[key] = hit
+        return hit
+
+    @torch.no_grad()
+    def denoise_step(self, latents, conditions, idx, timesteps, in_range=None):
+        """One iteration of the denoise loop (reference :2046-2090 /
+        :1496-1575): CFG batching, noise-predict forward, CFG combine, per-frame Euler
+        update and masked latent update.  `latents` fp32 [B,T,V,C,H,W] is updated in
+        place; idx int32 [B,T,V]; timesteps fp32 [B,T,V]."""
+        do_cfg = "guidance_scale" in self.inference_config
+        plan = self.sharding
+        x = latents
+        t = timesteps
+        split_cfg = do_cfg and plan is not None and plan.cfg_ways == 2
+        if do_cfg and not split_cfg:
+            x = torch.cat([latents, latents])
+            t = torch.cat([timesteps, timesteps])
+        self.model.shard = plan
+        tokens, _ = self.model.forward_tokens(
+            x, t, conditions["encoder_hidden_states"],
+            conditions["pooled_projections"],
+            conditions.get("condition_image_tensor"),
+            conditions.get("disable_crossview"),
+            conditions.get("disable_temporal"),
+            conditions.get("crossview_attention_mask"),
+            conditions.get("added_time_ids"),
+            t_offset=0 if plan is None else plan.t_offset,
+            T_total=None if plan is None else plan.T)
+        if split_cfg:   # exchange the branch predictions inside the CFG pair
+            both = getattr(self, "_cfg_tokens", None)
+            if both is None or both.shape[0] != 2 * tokens.shape[0]:
+                both = self._cfg_tokens = torch.empty(
+                    2 * tokens.shape[0], tokens.shape[1], device=tokens.device,
+                    dtype=tokens.dtype)
+            plan.gather_cfg_tokens(tokens, both)
+            tokens = both
+        sig = self.test_scheduler.sigmas
+        if sig.device != latents.device:
+            self.test_scheduler.sigmas = sig = sig.to(latents.device)
+        _ops.cfg_euler_step(
+            tokens, latents, idx, sig, cfg=2 if do_cfg else 1,
+            guidance_scale=self.inference_config.get("guidance_scale", 1),
+            patch=self.model.patch_size, in_range=in_range,
+            round_dtype=self.model_dtype)
+        return latents
+
+    def decode_latents(self, latents):
+        """latents [n, C, h, w] -> images via the supplied VAE (reference :2092-2101);
+        identity when no VAE object was configured."""
+        if self.vae is None:
+            return latents
+        shift = self.vae.config.shift_factor \
+            if self.vae.config.shift_factor is not None else 0
+        return self.vae.decode(
+            latents.to(dtype=self.vae.dtype) / self.vae.config.scaling_factor +
+            shift, return_dict=False)[0]
+
+
+class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
+
+    def reset_streaming(self, latent_shape, output_type):
+        assert self.common_config.get("frame_prediction_style") == \
+            "diffusion_forcing"
+        self.conditions = {}
+        self.condition_count = 0
+        self.latents = None
+        self.text_prompt_counter = 0
+        self.frames = []
+        self.latent_shape = tuple(latent_shape)
+        self.output_type = output_type
+        self.test_scheduler.set_timesteps(
+            self.inference_config["inference_steps"], self.device)
+        self.prev_ego_transforms = None
+        self._step_cache = {}
+
+    @torch.no_grad()
+    def inference_pipeline(self, latent_shape, start_timestep: int = 0,
+                           stop_timestep=None, take_time: int = 0):
+        """reference :2031-2103."""
+        steps = self.inference_config["inference_steps"]
+        assert steps % latent_shape[1] == 0
+        spi = steps // latent_shape[1]
+        B, T, V = latent_shape[:3]
+        latents = self.latents.to(torch.float32).contiguous()
+        stop_timestep = stop_timestep or steps
+        for i in range(start_timestep, stop_timestep):
+            idx, timesteps, in_range = self._df_step_tensors(
+                i, T, spi, take_time, B, V)
+            self.denoise_step(latents, self.conditions, idx, timesteps, in_range)
+        if stop_timestep >= steps:
+            self.frames.append(self.decode_latents(
+                latents[:, take_time].flatten(0, 1)))
+        return latents
+
+    @torch.no_grad()
+    def send_frame_condition(self, frame_condition_data):
+        """reference :2105-2219."""
+        do_cfg = "guidance_scale" in self.inference_config
+        steps = self.inference_config["inference_steps"]
+        spi = steps // self.latent_shape[1]
+        seq = self.inference_config["sequence_length_per_iteration"]
+        if frame_condition_data is None:      # flushing
+            assert self.condition_count == seq
+            for i in range(1, self.latent_shape[1]):
+                latents = self.inference_pipeline(
+                    self.latent_shape, start_timestep=steps + (i - 1) * spi,
+                    stop_timestep=steps + i * spi, take_time=i)
+                is_finished = torch.tensor(
+                    [j <= i for j in range(self.latent_shape[1])],
+                    device=self.device).view(1, -1, 1, 1, 1, 1)
+                self.latents = torch.where(is_finished, self.latents, latents)
+            return
+
+        fc = CrossviewTemporalSD.get_conditions(
+            self.model,
+            self.text_encoders if self.text_prompt_counter == 0 else None,
+            self.tokenizers, self.common_config,
+            (self.latent_shape[0], 1) + tuple(self.latent_shape[2:]),
+            frame_condition_data, self.device, self.model_dtype,
+            streaming_mode=True, prev_ego_transforms=self.prev_ego_transforms,
+            do_classifier_free_guidance=do_cfg)
+        if "ego_transforms" in frame_condition_data:
+            self.prev_ego_transforms = frame_condition_data["ego_transforms"]
+        if self.text_prompt_counter > 0:
+            fc["encoder_hidden_states"] = \
+                self.conditions["encoder_hidden_states"][:, -1:]
+            fc["pooled_projections"] = \
+                self.conditions["pooled_projections"][:, -1:]
+        self.text_prompt_counter = (self.text_prompt_counter + 1) % \
+            self.inference_config.get("text_prompt_interval", 1)
+        keep = self.inference_config[
+            "autoregression_condition_exception_for_take_sequence"]
+        noise_scale = getattr(self.test_scheduler, "init_noise_sigma", 1)
+        if self.condition_count < seq:        # gathering
+            for k, v in fc.items():
+                if k not in self.conditions or k in keep or v is None:
+                    self.conditions[k] = v
+                else:
+                    self.conditions[k] = torch.cat([self.conditions[k], v], dim=1)
+            self.condition_count += 1
+            if self.condition_count == seq:
+                self.latents = torch.randn(
+                    self.latent_shape, generator=self.generator)\
+                    .to(self.device) * noise_scale
+                self.latents = self.inference_pipeline(
+                    self.latent_shape, start_timestep=0, stop_timestep=steps)
+        else:                                  # streaming
+            for k, v in fc.items():
+                if k not in self.conditions or k in keep or v is None:
+                    self.conditions[k] = v
+                else:
+                    self.conditions[k] = torch.cat(
+                        [self.conditions[k][:, 1:], v], dim=1)
+            self.latents = torch.cat([
+                self.latents[:, 1:],
+                torch.randn((self.latent_shape[0], 1) + self.latent_shape[2:],
+                            generator=self.generator).to(self.device) *
+                noise_scale], 1)
+            self.latents = self.inference_pipeline(
+                self.latent_shape, start_timestep=steps - spi,
+                stop_timestep=steps)
+
+    def receive_frame(self):
+        if len(self.frames) == 0:
+            return None
+        return self.frames.pop(0)
+
+    def fifo_inference_pipeline(self, latent_shape, batch, output_type):
+        """reference :2234-2277."""
+        total_frame_count = batch["pts"].shape[1]
+        assert total_frame_count > \
+            self.inference_config["sequence_length_per_iteration"]
+        skip = self.inference_config[
+            "autoregression_data_exception_for_take_sequence"]
+        result = {"images": []}
+        self.reset_streaming(latent_shape, output_type)
+        for i in range(total_frame_count):
+            self.send_frame_condition({
+                k: (v if k in skip
+                    else dwm.functional.take_sequence_clip(v, i, i + 1))
+                for k, v in batch.items()})
+            image = self.receive_frame()
+            if image is not None:
+                result["images"].append(image)
+        self.send_frame_condition(None)
+        while True:
+            image = self.receive_frame()
+            if image is None:
+                break
+            result["images"].append(image)
+        if output_type == "pt":
+            result["images"] = torch.cat(result["images"])
+        return result
