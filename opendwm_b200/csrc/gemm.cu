@@ -2,14 +2,15 @@
 //
 //   D[M,N] = A[M,K] · W[N,K]^T     A, W 16-bit (bf16/fp16), fp32 accumulation in TMEM
 //
-// Roles (192 threads, one CTA per SM, persistent over output tiles):
+// Roles (320 threads, one CTA per SM, persistent over output tiles):
 //   warp 0    TMA producer: 128x64 A tile + 256x64 W tile per k-block into a
 //             4-stage 128B-swizzled shared-memory ring (mbarrier tx-count completion)
 //   warp 1    MMA issuer: one elected thread issues tcgen05.mma 128x256x16, commits
 //             stage release and accumulator-ready to mbarriers; owns TMEM alloc
-//   warps 2-5 epilogue: tcgen05.ld the 128x256 fp32 accumulator (lane = row), apply
-//             the fused epilogue and store; double-buffered TMEM (2 x 256 columns)
-//             so the epilogue of tile i overlaps the main loop of tile i+1
+//   warps 2-9 epilogue: tcgen05.ld the 128x256 fp32 accumulator (lane = row; two warps
+//             per TMEM lane quarter, interleaved over 32-column chunks), apply the fused
+//             epilogue and store; double-buffered TMEM (2 x 256 columns) so the
+//             epilogue of tile i overlaps the main loop of tile i+1
 //
 // Replaces the cuBLASLt GEMM + ~10 elementwise launches per sub-layer that the
 // reference runs.
@@ -26,9 +27,10 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;  // two warps per TMEM lane quarter, interleaved over column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;  // 4 epilogue warps x (32x32 fp32)
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 32 * 4;  // per epilogue warp: 32x32 fp32
 constexpr int GEMM_SMEM_BYTES =
     STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -87,7 +89,8 @@ __device__ __forceinline__ void stage_dump(float4* stg, int lane, const float (&
 
 template <typename T, int EPI>
 __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, int M,
-                                           int n_tile0, int N, const EpiParams& p, int lane) {
+                                           int n_tile0, int N, const EpiParams& p, int lane,
+                                           int half) {
   constexpr bool kOut16 = (EPI == DWM_EPI_STORE || EPI == DWM_EPI_GEGLU || EPI == DWM_EPI_QKNORM);
   const int rs = lane >> 3;  // phase-2: row within a group of 4
   const int c4 = lane & 7;   // phase-2: float4 column within the 32-col chunk
@@ -181,7 +184,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
 
   if constexpr (EPI == DWM_EPI_STORE || EPI == DWM_EPI_F32 || EPI == DWM_EPI_RESID) {
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = half; c < BN / 32; c += 2) {
       const int n0 = n_tile0 + c * 32;
       if (n0 >= N) break;
       prefetch32(n0);
@@ -193,12 +196,26 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       if (EPI != DWM_EPI_RESID) {
         if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.bias + n0 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
         }
-        if (p.act != DWM_ACT_NONE) {
+        // activation selected once per chunk (warp-uniform), loops fully unrolled
+        if (p.act == DWM_ACT_GELU_TANH) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        } else if (p.act == DWM_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+        } else if (p.act == DWM_ACT_GELU_ERF) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (p.act == DWM_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
       }
       stage_dump(stg, lane, v);
@@ -208,7 +225,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
     // tile columns [0,128) hold the value half, [128,256) the gate half of output
     // columns [n_tile0/2, n_tile0/2 + 128).
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = half; c < 4; c += 2) {
       uint32_t rv[32], rg[32];
       tmem_ld32(taddr + c * 32, rv);
       tmem_ld32(taddr + 128 + c * 32, rg);
@@ -230,7 +247,7 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
     }
   } else {  // DWM_EPI_QKNORM: 64-column heads
 #pragma unroll 1
-    for (int g = 0; g < BN / 64; ++g) {
+    for (int g = half; g < BN / 64; g += 2) {
       const int n0 = n_tile0 + g * 64;
       if (n0 >= N) break;
       uint32_t r0[32], r1[32];
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -373,7 +390,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -385,7 +402,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256, m_blk * BM + quarter * 32, M,
-                         n_blk * BN, N, p, lane);
+                         n_blk * BN, N, p, lane, (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
