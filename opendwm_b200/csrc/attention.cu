@@ -14,6 +14,8 @@
 // Flash-style streaming softmax, fp32 statistics; QK^T and PV run on mma.sync
 // m16n8k16 (tiles here are 16..602 long and the op is <4% of the step's FLOPs; the
 // tcgen05 pipeline is reserved for the projections/FFNs that dominate).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/dwm_b200.h"
 
@@ -331,6 +333,10 @@ static int launch_attn(const AttnParams& p, cudaStream_t s) {
   return 0;
 }
 
+// attention_tc.cu
+bool attn_tc_eligible(const dwm_attention_args* a);
+int attn_tc_launch(const dwm_attention_args* a, cudaStream_t s);
+
 }  // namespace dwm
 
 extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stream) {
@@ -348,6 +354,11 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
   if (a->split > 0)
     DWM_REQUIRE(a->out2 && a->ldo2 % 8 == 0 && a->split < a->seq, "dwm_b200_attention: bad split/out2");
   if (a->mask) DWM_REQUIRE(a->mask_div > 0 && a->n_outer > 0, "dwm_b200_attention: mask needs mask_div, n_outer");
+  {
+    // contiguous, unmasked sequences (joint / dual attention) run on tcgen05 + TMEM
+    static const bool legacy = getenv("DWM_ATTN_LEGACY") != nullptr;
+    if (!legacy && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
+  }
   const long long groups = static_cast<long long>(a->group_dims[0]) * a->group_dims[1] * a->group_dims[2];
   if (a->kv)
     DWM_REQUIRE(a->ld_kv % 8 == 0 && a->k_col % 8 == 0 && a->v_col % 8 == 0 && a->seq_kv > 0 && a->inner_kv > 0 &&

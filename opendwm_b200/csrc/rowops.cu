@@ -20,10 +20,12 @@ struct LnParams {
   void* out; long long ldo; void* out2; long long ldo2;
 };
 
-template <typename T, int VPL>
-__global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
+constexpr int LN_WARPS = 4;   // rows per block (one warp per row)
+
+template <typename T, int VPL, bool DUAL>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_kernel(const LnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * 8 + warp;
+  const int m = blockIdx.x * LN_WARPS + warp;
   if (m >= p.M) return;
   const int nvec = p.D >> 2;
   const int item = p.rows_per_item > 0 ? m / p.rows_per_item : 0;
@@ -31,20 +33,30 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const float4* ai = p.add_item ? reinterpret_cast<const float4*>(p.add_item + static_cast<long long>(item) * p.add_item_ld) : nullptr;
   const float4* af = p.add_full ? reinterpret_cast<const float4*>(p.add_full + static_cast<long long>(m) * p.add_full_ld) : nullptr;
   float4 v[VPL];
-  float sum = 0.f;
+  // all loads of the row are issued back to back (no control flow in between) so that
+  // VPL 16-byte requests per lane are in flight; the optional adds follow.
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      float4 t = xr[idx];
-      if (ai) { const float4 a = __ldg(ai + idx); t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
-      if (af) { const float4 a = af[idx]; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
-      v[i] = t;
-      sum += t.x + t.y + t.z + t.w;
-    } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (ai) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) { const float4 a = __ldg(ai + idx); v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
     }
   }
+  if (af) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) { const float4 a = af[idx]; v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w; }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) sum += v[i].x + v[i].y + v[i].z + v[i].w;
   if (p.sum_out) {
     float4* so = reinterpret_cast<float4*>(p.sum_out + static_cast<long long>(m) * p.ld_sum);
 #pragma unroll
@@ -71,42 +83,75 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LnParams p) {
   const float4* sh2 = p.shift2 ? reinterpret_cast<const float4*>(p.shift2 + static_cast<long long>(item) * p.mod_ld) : nullptr;
   const float4* sc2 = p.scale2 ? reinterpret_cast<const float4*>(p.scale2 + static_cast<long long>(item) * p.mod_ld) : nullptr;
   uint2* o1 = reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out) + static_cast<long long>(m) * p.ldo);
-  uint2* o2 = p.out2 ? reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out2) + static_cast<long long>(m) * p.ldo2) : nullptr;
+  uint2* o2 = DUAL ? reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.out2) + static_cast<long long>(m) * p.ldo2) : nullptr;
+  // Each optional vector is applied in its own fully unrolled loop so that its VPL loads
+  // are issued back to back (one exposed latency per vector instead of one per element).
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + 32 * i;
-    if (idx < nvec) {
-      float4 n;
-      n.x = (v[i].x - mean) * rstd; n.y = (v[i].y - mean) * rstd;
-      n.z = (v[i].z - mean) * rstd; n.w = (v[i].w - mean) * rstd;
-      if (w4) { const float4 w = __ldg(w4 + idx); n.x *= w.x; n.y *= w.y; n.z *= w.z; n.w *= w.w; }
-      if (b4) { const float4 b = __ldg(b4 + idx); n.x += b.x; n.y += b.y; n.z += b.z; n.w += b.w; }
-      float4 y = n;
-      if (sc) { const float4 s = __ldg(sc + idx); y.x *= 1.f + s.x; y.y *= 1.f + s.y; y.z *= 1.f + s.z; y.w *= 1.f + s.w; }
-      if (sh) { const float4 s = __ldg(sh + idx); y.x += s.x; y.y += s.y; y.z += s.z; y.w += s.w; }
-      uint2 pk; pk.x = Cvt<T>::pack2(y.x, y.y); pk.y = Cvt<T>::pack2(y.z, y.w);
-      o1[idx] = pk;
-      if (o2) {
-        float4 z = n;
-        if (sc2) { const float4 s = __ldg(sc2 + idx); z.x *= 1.f + s.x; z.y *= 1.f + s.y; z.z *= 1.f + s.z; z.w *= 1.f + s.w; }
-        if (sh2) { const float4 s = __ldg(sh2 + idx); z.x += s.x; z.y += s.y; z.z += s.z; z.w += s.w; }
-        uint2 pk2; pk2.x = Cvt<T>::pack2(z.x, z.y); pk2.y = Cvt<T>::pack2(z.z, z.w);
-        o2[idx] = pk2;
+    v[i].x = (v[i].x - mean) * rstd; v[i].y = (v[i].y - mean) * rstd;
+    v[i].z = (v[i].z - mean) * rstd; v[i].w = (v[i].w - mean) * rstd;
+  }
+  auto mul_vec = [&](float4 (&d)[VPL], const float4* src, float add_one) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float4 s = __ldg(src + idx);
+        d[i].x *= add_one + s.x; d[i].y *= add_one + s.y; d[i].z *= add_one + s.z; d[i].w *= add_one + s.w;
       }
     }
+  };
+  auto add_vec = [&](float4 (&d)[VPL], const float4* src) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        const float4 s = __ldg(src + idx);
+        d[i].x += s.x; d[i].y += s.y; d[i].z += s.z; d[i].w += s.w;
+      }
+    }
+  };
+  auto store_vec = [&](const float4 (&d)[VPL], uint2* dst) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        uint2 pk; pk.x = Cvt<T>::pack2(d[i].x, d[i].y); pk.y = Cvt<T>::pack2(d[i].z, d[i].w);
+        dst[idx] = pk;
+      }
+    }
+  };
+  if (w4) mul_vec(v, w4, 0.f);
+  if (b4) add_vec(v, b4);
+  if constexpr (DUAL) {   // second modulation of the same normalised row (SD35AdaLayerNormZeroX)
+    float4 z[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) z[i] = v[i];
+    if (sc2) mul_vec(z, sc2, 1.f);
+    if (sh2) add_vec(z, sh2);
+    store_vec(z, o2);
   }
+  if (sc) mul_vec(v, sc, 1.f);
+  if (sh) add_vec(v, sh);
+  store_vec(v, o1);
+}
+
+template <typename T, bool DUAL>
+static int launch_ln2(const LnParams& p, cudaStream_t s) {
+  const int need = (p.D / 4 + 31) / 32;
+  const unsigned grid = static_cast<unsigned>((p.M + LN_WARPS - 1) / LN_WARPS);
+  const int threads = LN_WARPS * 32;
+  if (need <= 3) layernorm_kernel<T, 3, DUAL><<<grid, threads, 0, s>>>(p);
+  else if (need <= 6) layernorm_kernel<T, 6, DUAL><<<grid, threads, 0, s>>>(p);
+  else if (need <= 12) layernorm_kernel<T, 12, DUAL><<<grid, threads, 0, s>>>(p);
+  else layernorm_kernel<T, 16, DUAL><<<grid, threads, 0, s>>>(p);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <typename T>
 static int launch_ln(const LnParams& p, cudaStream_t s) {
-  const int need = (p.D / 4 + 31) / 32;
-  const unsigned grid = static_cast<unsigned>((p.M + 7) / 8);
-  if (need <= 3) layernorm_kernel<T, 3><<<grid, 256, 0, s>>>(p);
-  else if (need <= 6) layernorm_kernel<T, 6><<<grid, 256, 0, s>>>(p);
-  else if (need <= 12) layernorm_kernel<T, 12><<<grid, 256, 0, s>>>(p);
-  else layernorm_kernel<T, 16><<<grid, 256, 0, s>>>(p);
-  DWM_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return p.out2 ? launch_ln2<T, true>(p, s) : launch_ln2<T, false>(p, s);
 }
 
 // ------------------------------------------------------------------ act + cast

@@ -104,3 +104,19 @@ def test_temporal(T, kind):
     ref = _ref(qkv, idx, D, heads)
     got = out.float()[idx.reshape(-1)].view(*idx.shape, D)
     assert ((got - ref).abs().max() / ref.abs().max()).item() < _tol(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("seq,N,heads", [(448, 5, 4), (129, 3, 2), (200, 7, 1), (640, 2, 3),
+                                         (65, 4, 2), (602, 40, 24)])
+def test_contiguous_sequences_tcgen05(seq, N, heads, dtype):
+    """Contiguous unmasked groups take the tcgen05/TMEM kernel (attention_tc.cu)."""
+    from opendwm_b200 import ops
+    D = heads * 64
+    qkv = _qkv(N * seq, D, dtype, seed=seq)
+    out = torch.zeros(N * seq, D, dtype=dtype, device="cuda")
+    ops.attention(qkv, out, D=D, heads=heads, group_dims=[N], group_strides=[seq], seq=seq)
+    idx = torch.arange(N * seq, device="cuda").view(N, seq)
+    ref = _ref(qkv, idx, D, heads)
+    err = ((out.view(N, seq, D).float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < _tol(dtype), err

@@ -1,0 +1,68 @@
+"""Isolated timings of the non-GEMM kernels at north-star shapes (B200)."""
+import json
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from opendwm_b200 import ops
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    res = {}
+    D, heads, N, S, L = 1536, 24, 192, 448, 154
+    dt = torch.bfloat16
+    # joint attention
+    qkv = torch.randn(N * (S + L), 3 * D, device="cuda").to(dt)
+    o = torch.empty(N * S, D, device="cuda", dtype=dt)
+    o2 = torch.empty(N * L, D, device="cuda", dtype=dt)
+    f = lambda: ops.attention(qkv, o, D=D, heads=heads, group_dims=[N], group_strides=[S + L],
+                              seq=S + L, out_group_strides=[S], out_stride_outer=0,
+                              out_stride_inner=1, split=S, out2=o2)
+    t = timeit(f)
+    fl = 4.0 * (S + L) ** 2 * D * N
+    res["joint_attention"] = dict(ms=t, tflops=fl / t / 1e9)
+    qs = torch.randn(N * S, 3 * D, device="cuda").to(dt)
+    f = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[N], group_strides=[S], seq=S)
+    t = timeit(f)
+    res["dual_attention"] = dict(ms=t, tflops=4.0 * S * S * D * N / t / 1e9)
+    # temporal pointwise (B'=2, T=16, V=6)
+    B, T, V = 2, 16, 6
+    f = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[B, V * S],
+                              group_strides=[T * V * S, 1], seq=T, inner=1, stride_outer=V * S,
+                              stride_inner=0)
+    t = timeit(f)
+    res["temporal_attention"] = dict(ms=t, gbs=(qs.numel() * 2 + o.numel() * 2) / t / 1e6)
+    # layernorm
+    x = torch.randn(N * S, D, device="cuda")
+    a16 = torch.empty(N * S, D, device="cuda", dtype=dt)
+    mod = torch.randn(N, 6 * D, device="cuda")
+    f = lambda: ops.layernorm(x, a16, eps=1e-6, rows_per_item=S, shift=mod[:, :D], scale=mod[:, D:2 * D])
+    t = timeit(f)
+    res["layernorm_mod"] = dict(ms=t, gbs=(x.numel() * 4 + a16.numel() * 2) / t / 1e6)
+    w, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    y = torch.empty_like(x)
+    emb = torch.randn(N, D, device="cuda")
+    f = lambda: ops.layernorm(x, a16, weight=w, bias=b, add_item=emb, rows_per_item=S, sum_out=y)
+    t = timeit(f)
+    res["layernorm_affine_sum"] = dict(ms=t, gbs=(x.numel() * 8 + a16.numel() * 2) / t / 1e6)
+    for k, v in res.items():
+        print(k, v, flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/kernel_bench.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
