@@ -95,6 +95,9 @@ typedef struct dwm_linear_args {
 
 const char* dwm_b200_version(void);
 const char* dwm_b200_last_error(void);
+/* Runtime switches: "gemm_2cta" = 1 routes dwm_b200_linear (M >= 512) to the 2-CTA
+ * cta_group::2 kernel, 0 to the 1-CTA kernel (default: env DWM_GEMM_2CTA, else 1). */
+int dwm_b200_set_option(const char* name, int value);
 
 /* y = epilogue(A @ W^T): replaces every torch.nn.Linear / 1x1 / patchify conv on the
  * path (diffusers Attention.to_q/k/v/to_out, FeedForward, AdaLayerNormZero.linear,

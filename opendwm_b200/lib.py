@@ -80,6 +80,7 @@ _lib = None
 SYMBOLS = {
     "dwm_b200_version": (ctypes.c_char_p, []),
     "dwm_b200_last_error": (ctypes.c_char_p, []),
+    "dwm_b200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
     "dwm_b200_linear": (ctypes.c_int, [ctypes.POINTER(LinearArgs), _p]),
     "dwm_b200_attention": (ctypes.c_int, [ctypes.POINTER(AttentionArgs), _p]),
     "dwm_b200_layernorm": (ctypes.c_int, [ctypes.POINTER(LayerNormArgs), _p]),
@@ -119,3 +120,7 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().dwm_b200_last_error().decode("utf-8", "replace")
         raise RuntimeError("{} failed (rc={}): {}".format(what, rc, msg))
+
+
+def set_option(name: str, value: int):
+    check(load().dwm_b200_set_option(name.encode(), int(value)), "dwm_b200_set_option")

@@ -6,6 +6,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["1cta", "2cta"])
+def gemm_variant(request):
+    """Every test runs on the 1-CTA kernel and on the cta_group::2 cluster kernel
+    (the latter is used for M >= 512)."""
+    from opendwm_b200 import lib
+    lib.set_option("gemm_2cta", 1 if request.param == "2cta" else 0)
+    yield
+    lib.set_option("gemm_2cta", 1)
+
+
 def _mk(shape, dtype, scale=1.0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
@@ -18,7 +28,7 @@ def _relerr(y, ref):
 SHAPES = [
     (128, 256, 64), (128, 256, 128), (256, 512, 1536), (192, 1536, 256),
     (448 * 3, 4608, 1536), (77, 320, 320), (1000, 64, 1536), (130, 288, 72),
-    (4096, 6144, 1536),
+    (4096, 6144, 1536), (700, 512, 192), (513, 288, 64),
 ]
 
 

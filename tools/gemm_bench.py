@@ -40,10 +40,13 @@ def main():
             kw = dict(epilogue=lib.EPI_QKNORM, q_norm_weight=qw, k_norm_weight=qw, qk_region=N // 3)
         out = ops.linear(a, w, **kw)
         kw.setdefault("out", out)
+        lib.set_option("gemm_2cta", 0)
         t = timeit(lambda: ops.linear(a, w, **kw))
+        lib.set_option("gemm_2cta", 1)
+        t2 = timeit(lambda: ops.linear(a, w, **kw))
         t_ref = timeit(lambda: torch.matmul(a, w.t()))
         fl = 2.0 * M * N * K
-        res.append(dict(M=M, N=N, K=K, epi=epi, ms=t, tflops=fl / t / 1e9,
+        res.append(dict(M=M, N=N, K=K, epi=epi, ms=t, tflops=fl / t / 1e9, tflops_2cta=fl / t2 / 1e9,
                         cublas_ms=t_ref, cublas_tflops=fl / t_ref / 1e9))
         print(res[-1], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
