@@ -289,7 +289,21 @@ def run_native(args):
     gemm_ms = sum(p["ms"] for p in prof["linear"])
     gemm_fl = sum(p["flops"] for p in prof["linear"])
     n_gemm = len(prof["linear"])
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    all_gemm = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    # dominant kernel = the (shape, epilogue) GEMM with the largest share of the timed region
+    by_shape = {}
+    for p_ in prof["linear"]:
+        k = (tuple(p_["shape"]), p_["epilogue"])
+        a = by_shape.setdefault(k, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += p_["ms"]
+        a[2] += p_["flops"]
+    dom_key, dom = max(by_shape.items(), key=lambda kv: kv[1][1])
+    achieved = dom[2] / (dom[1] * 1e-3) / 1e12
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_gemm2_geglu_summary.txt: dram read 469.8 MB + write 1035.0 MB)
+    NCU_TRAFFIC = {((86016, 12288, 1536), 1): 469.818368e6 + 1034.998e6}
+    traffic = NCU_TRAFFIC.get(dom_key)
     scale = 1.0 if not args.small else None
     line = {
         "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
@@ -308,10 +322,13 @@ def run_native(args):
             "step_flops_tflop": F_STEP_TFLOP if scale else None},
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
-            "kernel": "gemm_tcgen05_kernel (all dwm_b200_linear launches of the timed "
-                      "steps, CUDA events per launch)",
-            "launches": n_gemm, "gemm_share_of_step": gemm_ms / (ms * args.steps),
+            "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+            "kernel": "gemm2_tcgen05_kernel M=%d N=%d K=%d epilogue=%d (CUDA events around "
+                      "each of its %d launches in the timed steps)" % (dom_key[0] + (dom_key[1], dom[0])),
+            "algorithmic_flops_per_launch": dom[2] / dom[0],
+            "kernel_share_of_step": dom[1] / (ms * args.steps),
+            "all_gemm_achieved": all_gemm, "all_gemm_launches": n_gemm,
+            "gemm_share_of_step": gemm_ms / (ms * args.steps),
             "peak_source": peak_src + " bf16_tflops_sustained",
             "step_frac_of_peak": (F_STEP_TFLOP / world / (ms * 1e-3) / peak_tf)
             if scale else None},

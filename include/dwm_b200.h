@@ -230,6 +230,57 @@ int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int
                                    int64_t inner, const int32_t* idx, const float* sigmas,
                                    int n_sigmas, int round_dtype, dwm_stream_t stream);
 
+/* ---- convolution -------------------------------------------------------------------- */
+/* im2col-free convolution (implicit GEMM on tcgen05) over channels-last activations:
+ *   x      16-bit [nb, tp, h, w, c_in]   (tp includes the KT-1 leading causal frames)
+ *   weight 16-bit [kt*kh*kw, c_out, c_in] (tap-major: tap = (dt*kh + dh)*kw + dw)
+ *   out    rows = nb*(tp-kt+1)*h*w pixels, c_out columns (channels-last), pitch ldo
+ * spatial zero padding kh/2, kw/2; no implicit temporal padding.  c_out must be a multiple
+ * of 256, or exactly 128 or 32 (pad the weight rows).  Epilogues: DWM_EPI_STORE (16-bit,
+ * bias + act), DWM_EPI_F32, DWM_EPI_RESID (fp32: acc + bias + resid).
+ * Replaces diffusers CogVideoXCausalConv3d / CogVideoXUpsample3D.conv inside
+ * AutoencoderKLCogVideoX.decode (called at ctsd.py:1634-1640, 1615-1617) and the
+ * AdapterResnetBlock 3x3 convs (adapters.py:20). */
+typedef struct dwm_conv_args {
+  const void* x;
+  int64_t nb, tp, h, w, c_in;
+  const void* weight;
+  int kt, kh, kw;
+  int64_t c_out;
+  const float* bias;
+  int dtype;
+  int epilogue;
+  int act;
+  void* out;
+  int64_t ldo;
+  const float* resid;
+  int64_t ldr;
+} dwm_conv_args;
+
+int dwm_b200_conv(const dwm_conv_args* args, dwm_stream_t stream);
+
+/* ---- CogVideoX temporal-VAE decoder row kernels (channels-last fp32 activations) ------- */
+/* GroupNorm statistics: sums[n][g] = (sum, sum of squares) over the C/groups channels of
+ * group g and all `pixels` (= T*H*W) of volume n; `sums` (double [nb, groups, 2]) is zeroed
+ * here.  (diffusers CogVideoXSpatialNorm3D.norm_layer; statistics are per decode chunk.) */
+int dwm_b200_groupnorm_stats(const float* x, int64_t nb, int64_t pixels, int C, int groups,
+                             double* sums, dwm_stream_t stream);
+/* out16[n, out_t0 + t, h, w, c] = act( GN(x)*gamma+beta [ * zy[nearest] + zb[nearest] ] )
+ * with zy = conv_y(zq), zb = conv_b(zq) given at the latent resolution [nb, Tz, hz, wz, C]
+ * (nearest-neighbour lookup, first frame mapped separately when T is odd > 1).  Writes
+ * into a 16-bit channels-last buffer of out_T frames at frame offset out_t0 (the leading
+ * frames hold the causal-conv cache).  zy = zb = NULL gives plain GroupNorm (+SiLU). */
+int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
+                              int groups, const double* sums, float eps, const float* gamma,
+                              const float* beta, const float* zy, const float* zb, int Tz, int hz,
+                              int wz, int apply_silu, void* out, int64_t out_T, int64_t out_t0,
+                              int dtype, dwm_stream_t stream);
+/* CogVideoXUpsample3D interpolation: nearest x2 in H, W and (compress_time) in T, where an
+ * odd T > 1 keeps its first frame un-doubled in time; fp32 in, 16-bit out
+ * [nb, T', 2H, 2W, C]. */
+int dwm_b200_upsample_nearest(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
+                              int compress_time, void* out, int dtype, dwm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

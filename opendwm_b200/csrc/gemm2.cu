@@ -188,11 +188,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const int n_blk = tile % n_blocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      prefetch_resid_tile<EPI>(p, m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32 + lane, M, n_blk * BN, N, (warp - 2) >> 2);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
       drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256,
-                         m_blk * 2 * BM + static_cast<int>(rank) * BM + quarter * 32, M, n_blk * BN, N, p, lane,
+                         m_blk * 2 * BM + static_cast<int>(rank) * BM, quarter * 32, M, n_blk * BN, N, p, lane,
                          (warp - 2) >> 2);
       tc_fence_before();
       __syncwarp();

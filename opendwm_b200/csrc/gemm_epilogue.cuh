@@ -67,10 +67,22 @@ __device__ __forceinline__ void stage_dump(float4* stg, int lane, const float (&
   __syncwarp();
 }
 
+// Row mapping of an accumulator tile.  Linear (GEMM): tile row r is global row m_base + r,
+// valid while < M.  Pixel tile (implicit-GEMM convolution): the 128 accumulator rows are a
+// bw x bh patch of an image of width img_w; row r = (r / bw, r % bw) maps to global row
+// m_base + (r / bw) * img_w + r % bw and is valid inside the patch / image limits.
+struct TileGeom {
+  int bw;      // 0 => linear
+  int rows;    // bw * bh
+  int w_lim;   // img_w - w0
+  int h_lim;   // img_h - h0
+  int img_w;
+};
+
 template <typename T, int EPI>
-__device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, int M,
+__device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_base, int row0, int M,
                                            int n_tile0, int N, const EpiParams& p, int lane,
-                                           int half) {
+                                           int half, const TileGeom geom = TileGeom{0, 0, 0, 0, 0}) {
   constexpr bool kOut16 = (EPI == DWM_EPI_STORE || EPI == DWM_EPI_GEGLU || EPI == DWM_EPI_QKNORM);
   const int rs = lane >> 3;  // phase-2: row within a group of 4
   const int c4 = lane & 7;   // phase-2: float4 column within the 32-col chunk
@@ -83,8 +95,18 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
   const int rpi = static_cast<int>(p.rows_per_item);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int m = m0 + it * 4 + rs;
-    if (m < M) {
+    int m;
+    bool valid;
+    if (geom.bw > 0) {
+      const int r = row0 + it * 4 + rs;
+      const int ph = r / geom.bw, pw = r - ph * geom.bw;
+      valid = r < geom.rows && pw < geom.w_lim && ph < geom.h_lim;
+      m = m_base + ph * geom.img_w + pw;
+    } else {
+      m = m_base + row0 + it * 4 + rs;
+      valid = m < M;
+    }
+    if (valid) {
       int o = m;
       if (kOut16) {
         if (rpi > 0) o = (m / rpi) * static_cast<int>(p.out_item_stride) + (m % rpi);
@@ -268,6 +290,31 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m0, 
   }
 }
 
+
+// RESID epilogues read-modify-write a 128 KB fp32 tile whose HBM latency the 8 epilogue
+// warps cannot cover with register prefetch alone.  While the MMAs of the tile are still
+// running, each epilogue thread asks the L2 to fetch its row segment (512 B) of the
+// residual (and blend) operand, so the later loads hit L2.
+template <int EPI>
+__device__ __forceinline__ void prefetch_resid_tile(const EpiParams& p, int m, int M, int n_tile0,
+                                                    int N, int half) {
+  if constexpr (EPI == DWM_EPI_RESID) {
+    const int n0 = n_tile0 + half * (BN / 2);
+    if (m < M && n0 < N) {
+      const int cols = (N - n0) < (BN / 2) ? (N - n0) : (BN / 2);
+      const uint32_t bytes = static_cast<uint32_t>(cols) * 4u;
+      if (p.resid) {
+        const long long rr = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod) : m;
+        const float* src = p.resid + rr * p.ldr + n0;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      }
+      if (p.blend_x) {
+        const float* src = p.blend_x + static_cast<long long>(m) * p.ldx + n0;
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      }
+    }
+  }
+}
 
 // host side: fills EpiParams from the C-ABI struct
 inline void fill_epi_params(EpiParams& p, const dwm_linear_args* a) {

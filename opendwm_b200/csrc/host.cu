@@ -61,6 +61,29 @@ int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t col
   return 0;
 }
 
+int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled not available (no CUDA driver / GPU?)");
+    return -3;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstride[i] = strides_bytes[i];
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled (rank %d) failed (CUresult %d)", rank, (int)r);
+    return -3;
+  }
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

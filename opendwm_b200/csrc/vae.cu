@@ -1,0 +1,185 @@
+// HBM-bound kernels of the CogVideoX temporal-VAE decoder (channels-last activations):
+// GroupNorm statistics, the fused SpatialNorm3D (GroupNorm * conv_y(zq) + conv_b(zq)) +
+// SiLU that writes the 16-bit, causally time-padded input of the next convolution, and
+// the nearest-neighbour (space / space-time) upsampler.
+#include "common.cuh"
+#include "../../include/dwm_b200.h"
+
+namespace dwm {
+
+// ---- GroupNorm statistics: sums[n][g] = (sum x, sum x^2) over (C/G channels, all pixels) ----
+// block = 256 threads; thread handles float4 channel vector c4 = tid % (C/4) of pixels
+// tid / (C/4), +stride...  Partial sums are combined per group in shared memory, then one
+// double atomicAdd per (block, group).
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, long long pixels, int C, int G,
+                                                       long long pixels_per_block, double* __restrict__ sums) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int n = blockIdx.y;
+  const int vec = C >> 2;
+  const int tid = threadIdx.x;
+  if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  __syncthreads();
+  const int c4 = tid % vec;
+  const int prow = tid / vec;
+  const int rows_per_iter = 256 / vec;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pixels_per_block;
+  long long p1 = p0 + pixels_per_block;
+  if (p1 > pixels) p1 = pixels;
+  float a = 0.f, b = 0.f;
+  if (prow < rows_per_iter) {
+    const float4* base = reinterpret_cast<const float4*>(x + static_cast<long long>(n) * pixels * C);
+    for (long long p = p0 + prow; p < p1; p += rows_per_iter) {
+      const float4 v = base[p * vec + c4];
+      a += v.x + v.y + v.z + v.w;
+      b += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  const int g = (c4 * 4) / (C / G);
+  atomicAdd(&s_sum[g], a);
+  atomicAdd(&s_sq[g], b);
+  __syncthreads();
+  if (tid < G) {
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2], static_cast<double>(s_sum[tid]));
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2 + 1], static_cast<double>(s_sq[tid]));
+  }
+}
+
+// ---- SpatialNorm3D / GroupNorm apply (+SiLU) -> 16-bit, written at a frame offset ----
+struct SnParams {
+  const float* x; int nb, T, H, W, C, G;
+  const double* sums; float eps;
+  const float* gamma; const float* beta;
+  const float* zy; const float* zb; int Tz, hz, wz;
+  int silu;
+  void* out; int out_T, out_t0;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
+  const int vec = p.C >> 2;
+  const long long total = static_cast<long long>(p.nb) * p.T * p.H * p.W * vec;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = static_cast<int>(i % vec);
+  long long r = i / vec;
+  const int w = static_cast<int>(r % p.W); r /= p.W;
+  const int h = static_cast<int>(r % p.H); r /= p.H;
+  const int t = static_cast<int>(r % p.T);
+  const int n = static_cast<int>(r / p.T);
+  const int g = (c4 * 4) / (p.C / p.G);
+  const double cnt = static_cast<double>(p.C / p.G) * p.T * p.H * p.W;
+  const double s = p.sums[(static_cast<long long>(n) * p.G + g) * 2];
+  const double ss = p.sums[(static_cast<long long>(n) * p.G + g) * 2 + 1];
+  const double mean_d = s / cnt;
+  const float mean = static_cast<float>(mean_d);
+  const float rstd = rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps);
+  float4 v = reinterpret_cast<const float4*>(p.x)[i];
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+  v.x = (v.x - mean) * rstd * ga.x + be.x;
+  v.y = (v.y - mean) * rstd * ga.y + be.y;
+  v.z = (v.z - mean) * rstd * ga.z + be.z;
+  v.w = (v.w - mean) * rstd * ga.w + be.w;
+  if (p.zy) {
+    // nearest-neighbour position in the latent grid; odd T > 1 treats the first frame apart
+    int tz;
+    if (p.T > 1 && (p.T & 1)) tz = t == 0 ? 0 : 1 + ((t - 1) * (p.Tz - 1)) / (p.T - 1);
+    else tz = (t * p.Tz) / p.T;
+    const int hq = (h * p.hz) / p.H, wq = (w * p.wz) / p.W;
+    const long long zi = (((static_cast<long long>(n) * p.Tz + tz) * p.hz + hq) * p.wz + wq) * vec + c4;
+    const float4 y = __ldg(reinterpret_cast<const float4*>(p.zy) + zi);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.zb) + zi);
+    v.x = v.x * y.x + b.x; v.y = v.y * y.y + b.y; v.z = v.z * y.z + b.z; v.w = v.w * y.w + b.w;
+  }
+  if (p.silu) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+  const long long o = (((static_cast<long long>(n) * p.out_T + p.out_t0 + t) * p.H + h) * p.W + w) * vec + c4;
+  uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
+  reinterpret_cast<uint2*>(p.out)[o] = pk;
+}
+
+// ---- nearest upsample x2 in space, optionally in time (CogVideoXUpsample3D rules) ----
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_kernel(const float* __restrict__ x, int nb, int Ti, int H, int W, int C,
+                                                       int To, int mode, T* __restrict__ out) {
+  // mode 0: space only; 1: space+time all frames; 2: first frame space only, rest space+time
+  const int vec = C >> 2;
+  const long long total = static_cast<long long>(nb) * To * (2 * H) * (2 * W) * vec;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c4 = static_cast<int>(i % vec);
+  long long r = i / vec;
+  const int w = static_cast<int>(r % (2 * W)); r /= 2 * W;
+  const int h = static_cast<int>(r % (2 * H)); r /= 2 * H;
+  const int t = static_cast<int>(r % To);
+  const int n = static_cast<int>(r / To);
+  int ti;
+  if (mode == 0) ti = t;
+  else if (mode == 1) ti = t >> 1;
+  else ti = t == 0 ? 0 : 1 + ((t - 1) >> 1);
+  const float4 v = reinterpret_cast<const float4*>(x)[(((static_cast<long long>(n) * Ti + ti) * H + (h >> 1)) * W + (w >> 1)) * vec + c4];
+  uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
+  reinterpret_cast<uint2*>(out)[i] = pk;
+}
+
+}  // namespace dwm
+
+using namespace dwm;
+
+extern "C" int dwm_b200_groupnorm_stats(const float* x, int64_t nb, int64_t pixels, int C, int groups,
+                                        double* sums, dwm_stream_t stream) {
+  DWM_REQUIRE(x && sums && nb > 0 && pixels > 0, "dwm_b200_groupnorm_stats: bad arguments");
+  DWM_REQUIRE(C % 4 == 0 && C / 4 <= 256 && groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 &&
+                  256 % (C / 4) == 0,
+              "dwm_b200_groupnorm_stats: need C %% (4*groups) == 0, C/4 a divisor of 256 (got C=%d, groups=%d)", C, groups);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  DWM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * nb * groups, s));
+  const long long ppb = 1024;
+  dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
+  gn_stats_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
+                                         int groups, const double* sums, float eps, const float* gamma,
+                                         const float* beta, const float* zy, const float* zb, int Tz, int hz,
+                                         int wz, int apply_silu, void* out, int64_t out_T, int64_t out_t0,
+                                         int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(x && sums && gamma && beta && out, "dwm_b200_spatialnorm_silu: null pointer");
+  DWM_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0, "dwm_b200_spatialnorm_silu: bad C/groups");
+  DWM_REQUIRE((zy == nullptr) == (zb == nullptr), "dwm_b200_spatialnorm_silu: zy and zb go together");
+  DWM_REQUIRE(out_t0 >= 0 && out_t0 + T <= out_T, "dwm_b200_spatialnorm_silu: frame window outside out buffer");
+  SnParams p;
+  p.x = x; p.nb = (int)nb; p.T = (int)T; p.H = (int)H; p.W = (int)W; p.C = C; p.G = groups;
+  p.sums = sums; p.eps = eps; p.gamma = gamma; p.beta = beta; p.zy = zy; p.zb = zb;
+  p.Tz = Tz; p.hz = hz; p.wz = wz; p.silu = apply_silu; p.out = out; p.out_T = (int)out_T; p.out_t0 = (int)out_t0;
+  const long long total = nb * T * H * W * (C / 4);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DWM_BF16) spatialnorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
+  else if (dtype == DWM_F16) spatialnorm_kernel<__half><<<grid, 256, 0, s>>>(p);
+  else { set_last_error("dwm_b200_spatialnorm_silu: bad dtype"); return -1; }
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_upsample_nearest(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
+                                         int compress_time, void* out, int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(x && out && C % 4 == 0, "dwm_b200_upsample_nearest: bad arguments");
+  int mode = 0;
+  long long To = T;
+  if (compress_time && T > 1) {
+    if (T % 2 == 1) { mode = 2; To = 1 + 2 * (T - 1); }
+    else { mode = 1; To = 2 * T; }
+  }
+  const long long total = nb * To * 2 * H * 2 * W * (C / 4);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == DWM_BF16)
+    upsample_kernel<<<grid, 256, 0, s>>>(x, (int)nb, (int)T, (int)H, (int)W, C, (int)To, mode, reinterpret_cast<__nv_bfloat16*>(out));
+  else if (dtype == DWM_F16)
+    upsample_kernel<<<grid, 256, 0, s>>>(x, (int)nb, (int)T, (int)H, (int)W, C, (int)To, mode, reinterpret_cast<__half*>(out));
+  else { set_last_error("dwm_b200_upsample_nearest: bad dtype"); return -1; }
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

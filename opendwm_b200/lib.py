@@ -74,6 +74,18 @@ class LayerNormArgs(ctypes.Structure):
     ]
 
 
+class ConvArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", _p), ("nb", _i64), ("tp", _i64), ("h", _i64), ("w", _i64),
+        ("c_in", _i64),
+        ("weight", _p), ("kt", ctypes.c_int), ("kh", ctypes.c_int),
+        ("kw", ctypes.c_int), ("c_out", _i64),
+        ("bias", _p), ("dtype", ctypes.c_int), ("epilogue", ctypes.c_int),
+        ("act", ctypes.c_int),
+        ("out", _p), ("ldo", _i64), ("resid", _p), ("ldr", _i64),
+    ]
+
+
 _lib = None
 
 # name -> (restype, argtypes); every symbol include/dwm_b200.h declares.
@@ -94,6 +106,15 @@ SYMBOLS = {
         _p, _i64, ctypes.c_int, ctypes.c_float, _i64, _i64, _i64, ctypes.c_int,
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _p, _p, ctypes.c_int, _p, _p,
         _p, ctypes.c_int, _p]),
+    "dwm_b200_conv": (ctypes.c_int, [ctypes.POINTER(ConvArgs), _p]),
+    "dwm_b200_groupnorm_stats": (ctypes.c_int, [_p, _i64, _i64, ctypes.c_int,
+                                                ctypes.c_int, _p, _p]),
+    "dwm_b200_spatialnorm_silu": (ctypes.c_int, [
+        _p, _i64, _i64, _i64, _i64, ctypes.c_int, ctypes.c_int, _p, ctypes.c_float,
+        _p, _p, _p, _p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _p,
+        _i64, _i64, ctypes.c_int, _p]),
+    "dwm_b200_upsample_nearest": (ctypes.c_int, [
+        _p, _i64, _i64, _i64, _i64, ctypes.c_int, ctypes.c_int, _p, ctypes.c_int, _p]),
     "dwm_b200_euler_step_by_indices": (ctypes.c_int, [
         _p, _p, _i64, _i64, _p, _p, ctypes.c_int, ctypes.c_int, _p]),
 }

@@ -320,3 +320,99 @@ def euler_step_by_indices(model_output, sample, idx, sigmas, round_dtype=torch.f
         sigmas.data_ptr(), sigmas.numel(), _code(round_dtype), _stream()),
         "dwm_b200_euler_step_by_indices")
     return sample
+
+
+def pack_conv_weight(weight: torch.Tensor, dtype, pad_out_to=None, pad_in_to=None):
+    """torch Conv3d/Conv2d weight [O, I, (kt,) kh, kw] -> tap-major [kt*kh*kw, O', I']
+    (optionally zero-padding O / I)."""
+    if weight.dim() == 4:
+        weight = weight.unsqueeze(2)
+    o, i, kt, kh, kw = weight.shape
+    w = weight.detach().permute(2, 3, 4, 0, 1).reshape(kt * kh * kw, o, i)
+    op = pad_out_to or o
+    ip = pad_in_to or i
+    if op != o or ip != i:
+        wp = torch.zeros(kt * kh * kw, op, ip, device=w.device, dtype=w.dtype)
+        wp[:, :o, :i] = w
+        w = wp
+    return w.to(dtype).contiguous()
+
+
+def conv(x, weight, bias=None, *, kernel, epilogue=_l.EPI_F32, act=_l.ACT_NONE,
+         out=None, resid=None):
+    """x: 16-bit channels-last [nb, tp, h, w, c_in]; weight: tap-major
+    [kt*kh*kw, c_out, c_in]; returns [nb*(tp-kt+1)*h*w, c_out]."""
+    if x.dim() != 5 or not x.is_contiguous() or not weight.is_contiguous():
+        raise ValueError("conv: x must be contiguous [nb, tp, h, w, c]")
+    if not x.is_cuda:
+        raise RuntimeError("dwm_b200 kernels need CUDA tensors (no CPU fallback)")
+    kt, kh, kw = kernel
+    nb, tp, h, w, c_in = x.shape
+    taps, c_out, c_in2 = weight.shape
+    if taps != kt * kh * kw or c_in2 != c_in or weight.dtype != x.dtype:
+        raise ValueError("conv: weight shape/dtype mismatch")
+    rows = nb * (tp - kt + 1) * h * w
+    want = x.dtype if epilogue == _l.EPI_STORE else torch.float32
+    if out is None:
+        out = torch.empty(rows, c_out, device=x.device, dtype=want)
+    _rows2d(out, "out")
+    if out.dtype != want or out.shape[0] < rows:
+        raise TypeError("conv: bad out tensor")
+    a = _l.ConvArgs()
+    a.x, a.nb, a.tp, a.h, a.w, a.c_in = x.data_ptr(), nb, tp, h, w, c_in
+    a.weight, a.kt, a.kh, a.kw, a.c_out = weight.data_ptr(), kt, kh, kw, c_out
+    a.bias = _ptr(_f32(bias, "bias"))
+    a.dtype, a.epilogue, a.act = _dt(x), epilogue, act
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    if resid is not None:
+        _rows2d(_f32(resid, "resid"), "resid")
+        a.resid, a.ldr = resid.data_ptr(), resid.stride(0)
+    _l.check(_l.load().dwm_b200_conv(ctypes.byref(a), _stream()), "dwm_b200_conv")
+    return out
+
+
+def groupnorm_stats(x, groups, sums=None):
+    """x fp32 channels-last [nb, T, H, W, C] -> double [nb, groups, 2] (sum, sum sq)."""
+    _f32(x, "x")
+    if x.dim() != 5 or not x.is_contiguous():
+        raise ValueError("x must be contiguous [nb, T, H, W, C]")
+    nb, T, H, W, C = x.shape
+    if sums is None:
+        sums = torch.empty(nb, groups, 2, device=x.device, dtype=torch.float64)
+    _l.check(_l.load().dwm_b200_groupnorm_stats(
+        x.data_ptr(), nb, T * H * W, C, groups, sums.data_ptr(), _stream()),
+        "dwm_b200_groupnorm_stats")
+    return sums
+
+
+def spatialnorm_silu(x, sums, gamma, beta, out, *, groups, eps=1e-6, zy=None,
+                     zb=None, out_t0=0, silu=True):
+    """x fp32 [nb,T,H,W,C]; out 16-bit [nb,out_T,H,W,C]; zy/zb fp32 [nb,Tz,hz,wz,C]."""
+    _f32(x, "x")
+    nb, T, H, W, C = x.shape
+    if out.dim() != 5 or not out.is_contiguous() or out.shape[2:] != x.shape[2:]:
+        raise ValueError("out must be contiguous [nb, out_T, H, W, C]")
+    Tz = hz = wz = 0
+    if zy is not None:
+        _f32(zy, "zy")
+        _f32(zb, "zb")
+        Tz, hz, wz = zy.shape[1:4]
+    _l.check(_l.load().dwm_b200_spatialnorm_silu(
+        x.data_ptr(), nb, T, H, W, C, groups, sums.data_ptr(), eps,
+        _f32(gamma, "gamma").data_ptr(), _f32(beta, "beta").data_ptr(),
+        _ptr(zy), _ptr(zb), Tz, hz, wz, int(silu), out.data_ptr(), out.shape[1],
+        out_t0, _dt(out), _stream()), "dwm_b200_spatialnorm_silu")
+    return out
+
+
+def upsample_nearest(x, compress_time, dtype):
+    _f32(x, "x")
+    nb, T, H, W, C = x.shape
+    To = T
+    if compress_time and T > 1:
+        To = 1 + 2 * (T - 1) if T % 2 == 1 else 2 * T
+    out = torch.empty(nb, To, 2 * H, 2 * W, C, device=x.device, dtype=dtype)
+    _l.check(_l.load().dwm_b200_upsample_nearest(
+        x.data_ptr(), nb, T, H, W, C, int(compress_time), out.data_ptr(), _dt(out),
+        _stream()), "dwm_b200_upsample_nearest")
+    return out

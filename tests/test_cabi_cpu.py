@@ -34,7 +34,8 @@ def test_struct_layouts_match_header_field_order():
         text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
     for cname, st in (("dwm_linear_args", lib.LinearArgs),
                       ("dwm_attention_args", lib.AttentionArgs),
-                      ("dwm_layernorm_args", lib.LayerNormArgs)):
+                      ("dwm_layernorm_args", lib.LayerNormArgs),
+                      ("dwm_conv_args", lib.ConvArgs)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), text, re.S).group(1)
         fields = []
         for decl in body.split(";"):

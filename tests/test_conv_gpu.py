@@ -1,0 +1,58 @@
+"""Parity of the im2col-free tcgen05 convolution against torch conv3d (fp32) on the same
+16-bit inputs: CogVideoX causal 3x3x3, per-frame 1x3x3, 3x3 adapter conv, ragged tiles."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(nb, t_out, h, w, cin, cout, kernel, dtype, epilogue="f32", seed=0):
+    from opendwm_b200 import ops, lib
+    kt, kh, kw = kernel
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(nb, cin, t_out + kt - 1, h, w, generator=g).to(dtype).cuda()   # NCTHW, time-padded
+    wt = (torch.randn(cout, cin, kt, kh, kw, generator=g) * (cin * kt * kh * kw) ** -0.5).to(dtype).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    ref = torch.nn.functional.conv3d(x.float(), wt.float(), b, padding=(0, kh // 2, kw // 2))
+    ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)                              # channels-last rows
+    cin_p = (cin + 7) // 8 * 8
+    cout_p = cout if (cout % 256 == 0 or cout in (128, 32)) else (32 if cout < 32 else None)
+    xcl = torch.zeros(nb, t_out + kt - 1, h, w, cin_p, dtype=dtype, device="cuda")
+    xcl[..., :cin] = x.permute(0, 2, 3, 4, 1)
+    wp = ops.pack_conv_weight(wt, dtype, pad_out_to=cout_p, pad_in_to=cin_p)
+    bp = torch.zeros(cout_p, device="cuda")
+    bp[:cout] = b
+    if epilogue == "f32":
+        y = ops.conv(xcl, wp, bp, kernel=kernel, epilogue=lib.EPI_F32)[:, :cout]
+    elif epilogue == "resid":
+        r = torch.randn(ref.shape[0], cout_p, generator=g).cuda()
+        y = ops.conv(xcl, wp, bp, kernel=kernel, epilogue=lib.EPI_RESID, resid=r)[:, :cout]
+        ref = ref + r[:, :cout]
+    else:
+        y = ops.conv(xcl, wp, bp, kernel=kernel, epilogue=lib.EPI_STORE, act=lib.ACT_SILU)[:, :cout].float()
+        ref = torch.nn.functional.silu(ref)
+    return ((y - ref).abs().max() / ref.abs().max()).item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_causal_conv3d_3x3x3(dtype):
+    assert _case(2, 3, 8, 14, 64, 256, (3, 3, 3), dtype) < 2e-5 * 50
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 2, 32, 56, 128, 128, (3, 3, 3)),    # bw 56, bh 2
+    (1, 1, 16, 112, 64, 128, (1, 3, 3)),    # bw 112
+    (1, 1, 6, 224, 64, 256, (1, 3, 3)),     # W > 128: ragged second tile
+    (2, 1, 16, 28, 192, 512, (1, 3, 3)),    # adapter-like, 2 N tiles
+    (1, 2, 5, 9, 16, 32, (3, 3, 3)),        # tiny ragged, C_in padded... c_out 32
+    (1, 1, 7, 130, 72, 3, (1, 3, 3)),       # conv_out-like: C_out 3 padded to 32
+    (3, 1, 4, 4, 64, 128, (1, 1, 1)),       # 1x1x1
+])
+def test_shapes(shape):
+    err = _case(*shape, torch.bfloat16)
+    assert err < 1e-3, err
+
+
+def test_epilogues():
+    assert _case(1, 2, 16, 56, 128, 256, (3, 3, 3), torch.bfloat16, "resid") < 1e-3
+    assert _case(1, 2, 16, 56, 128, 128, (3, 3, 3), torch.bfloat16, "store") < 8e-3

@@ -21,11 +21,14 @@ def timeit(fn, iters=10, warm=3):
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
     shapes = [(86016, 12288, 1536, "geglu"), (86016, 1536, 6144, "resid"),
               (86016, 4608, 1536, "qknorm"), (86016, 1536, 1536, "resid"),
               (86016, 6144, 1536, "store"), (29568, 4608, 1536, "store"),
               (8192, 8192, 8192, "store")]
     res = []
+    if only:
+        shapes = [s for s in shapes if s[3] == only][:1]
     for M, N, K, epi in shapes:
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = (torch.randn(N, K, device="cuda") * 0.03).bfloat16()
