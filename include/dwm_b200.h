@@ -91,6 +91,13 @@ typedef struct dwm_linear_args {
   int64_t ldx;
   const float* alpha;   /* fp32 [batches]; b(m) = m / rows_per_batch */
   int64_t rows_per_batch;
+  /* fused compute + collective (16-bit epilogues): every output tile is ALSO stored to
+   * the same element offset of n_peer_out peer buffers (device pointers into other GPUs'
+   * memory, NVLink P2P / symmetric memory).  Used to scatter the K,V projection of a
+   * frame shard straight into every peer's gathered K,V buffer, replacing GEMM +
+   * all-gather by one kernel. */
+  void* peer_out[8];
+  int n_peer_out;
 } dwm_linear_args;
 
 const char* dwm_b200_version(void);
@@ -236,7 +243,7 @@ int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int
  *   weight 16-bit [kt*kh*kw, c_out, c_in] (tap-major: tap = (dt*kh + dh)*kw + dw)
  *   out    rows = nb*(tp-kt+1)*h*w pixels, c_out columns (channels-last), pitch ldo
  * spatial zero padding kh/2, kw/2; no implicit temporal padding.  c_out must be a multiple
- * of 256, or exactly 128 or 32 (pad the weight rows).  Epilogues: DWM_EPI_STORE (16-bit,
+ * of 256, or exactly 128, 64 or 32 (pad the weight rows).  Epilogues: DWM_EPI_STORE (16-bit,
  * bias + act), DWM_EPI_F32, DWM_EPI_RESID (fp32: acc + bias + resid).
  * Replaces diffusers CogVideoXCausalConv3d / CogVideoXUpsample3D.conv inside
  * AutoencoderKLCogVideoX.decode (called at ctsd.py:1634-1640, 1615-1617) and the

@@ -197,6 +197,7 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
   p.out = a->out; p.ldo = a->ldo; p.bias = a->bias; p.act = a->act;
   p.resid = a->resid; p.ldr = a->ldr;
   p.norm_regions = 2;
+  p.n_peers = 0;
 
   auto kern = conv_tcgen05_kernel<T, EPI, CBN>;
   constexpr int smem_bytes = CV_STAGES * (CV_A_BYTES + CBN * BK * 2) + EPI_STAGE_BYTES + 1024 + 256;
@@ -218,8 +219,9 @@ template <typename T, int EPI>
 static int conv_pick_bn(const dwm_conv_args* a, cudaStream_t s) {
   if (a->c_out % 256 == 0) return launch_conv<T, EPI, 256>(a, s);
   if (a->c_out == 128) return launch_conv<T, EPI, 128>(a, s);
+  if (a->c_out == 64) return launch_conv<T, EPI, 64>(a, s);
   if (a->c_out == 32) return launch_conv<T, EPI, 32>(a, s);
-  set_last_error("dwm_b200_conv: C_out must be a multiple of 256, or 128, or 32 (pad); got %lld", (long long)a->c_out);
+  set_last_error("dwm_b200_conv: C_out must be a multiple of 256, or 128 / 64 / 32 (pad); got %lld", (long long)a->c_out);
   return -1;
 }
 

@@ -237,6 +237,10 @@ extern "C" int dwm_b200_linear(const dwm_linear_args* a, dwm_stream_t stream) {
                     (a->k_norm_weight || a->qk_norm_regions == 1),
                 "dwm_b200_linear: QKNORM needs head_dim 64 regions and both norm weights");
   }
+  DWM_REQUIRE(a->n_peer_out >= 0 && a->n_peer_out <= 8, "dwm_b200_linear: n_peer_out out of range");
+  if (a->n_peer_out > 0)
+    DWM_REQUIRE(a->epilogue == DWM_EPI_STORE || a->epilogue == DWM_EPI_QKNORM || a->epilogue == DWM_EPI_GEGLU,
+                "dwm_b200_linear: peer_out needs a 16-bit epilogue");
   if (a->epilogue == DWM_EPI_RESID && a->blend_x)
     DWM_REQUIRE(a->alpha != nullptr, "dwm_b200_linear: blend_x without alpha");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);

@@ -33,6 +33,8 @@ struct EpiParams {
   long long ldx;
   const float* alpha;
   long long rows_per_batch;
+  void* peer_out[8];
+  int n_peers;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -135,6 +137,10 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_ba
         pk.x = Cvt<T>::pack2(v.x, v.y);
         pk.y = Cvt<T>::pack2(v.z, v.w);
         *reinterpret_cast<uint2*>(dst) = pk;
+        // fused scatter to the peers' buffers over NVLink (same element offset)
+        const long long eoff = static_cast<long long>(orow[it]) * p.ldo + ocol + c4 * 4;
+        for (int q = 0; q < p.n_peers; ++q)
+          *reinterpret_cast<uint2*>(reinterpret_cast<T*>(p.peer_out[q]) + eoff) = pk;
       }
     }
   };
@@ -339,6 +345,8 @@ inline void fill_epi_params(EpiParams& p, const dwm_linear_args* a) {
   p.ldx = a->ldx;
   p.alpha = a->alpha;
   p.rows_per_batch = a->rows_per_batch;
+  p.n_peers = a->n_peer_out;
+  for (int i = 0; i < 8; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
 }
 
 }  // namespace dwm

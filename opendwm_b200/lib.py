@@ -34,6 +34,7 @@ class LinearArgs(ctypes.Structure):
         ("gate", _p), ("gate_ld", _i64),
         ("blend_x", _p), ("ldx", _i64),
         ("alpha", _p), ("rows_per_batch", _i64),
+        ("peer_out", _p * 8), ("n_peer_out", ctypes.c_int),
     ]
 
 

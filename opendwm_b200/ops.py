@@ -65,7 +65,7 @@ def _rows2d(t, name):
 def linear(a, w, bias=None, *, epilogue=_l.EPI_STORE, act=_l.ACT_NONE,
            out=None, rows_per_item=0, out_item_stride=0, out_row_offset=0,
            q_norm_weight=None, k_norm_weight=None, qk_region=0, eps=1e-6,
-           qk_norm_regions=0, resid=None, resid_row_mod=0, gate=None, blend_x=None, alpha=None,
+           qk_norm_regions=0, peer_out=None, resid=None, resid_row_mod=0, gate=None, blend_x=None, alpha=None,
            rows_per_batch=0):
     """out = epilogue(a @ w.T).  a [M,K], w [N,K] 16-bit; see include/dwm_b200.h."""
     _rows2d(a, "a")
@@ -118,6 +118,13 @@ def linear(a, w, bias=None, *, epilogue=_l.EPI_STORE, act=_l.ACT_NONE,
         args.blend_x, args.ldx = blend_x.data_ptr(), blend_x.stride(0)
     args.alpha = _ptr(_f32(alpha, "alpha"))
     args.rows_per_batch = rows_per_batch
+    if peer_out:
+        # raw device pointers of the peers' buffers (same layout / pitch as `out`)
+        if len(peer_out) > 8:
+            raise ValueError("at most 8 peer buffers")
+        for i, ptr in enumerate(peer_out):
+            args.peer_out[i] = int(ptr)
+        args.n_peer_out = len(peer_out)
     if _prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)

@@ -34,6 +34,10 @@ class ShardPlan:
         self.T_loc = frames // self.t_ways
         self.t_offset = self.t_rank * self.T_loc
         self.t_group = self.cfg_group = None
+        # K,V exchange of the temporal blocks: fused GEMM-epilogue scatter into peer
+        # (symmetric) memory by default, NCCL all-gather with DWM_PEER_SCATTER=0
+        import os
+        self.use_peer_scatter = os.environ.get("DWM_PEER_SCATTER", "1") != "0"
         if make_groups and world > 1:
             # every rank must take part in creating every group
             for c in range(self.cfg_ways):
@@ -70,7 +74,8 @@ class ShardPlan:
         return out
 
     def local_latents(self, latents):
-        return latents[:, self.frame_slice()].contiguous()
+        """Copy of this rank's frames (always a new tensor: steps update it in place)."""
+        return latents[:, self.frame_slice()].clone(memory_format=torch.contiguous_format)
 
     # ---- collectives -------------------------------------------------------------------
     def gather_frames_kv(self, kv_local: torch.Tensor, kv_all: torch.Tensor,
@@ -92,3 +97,39 @@ class ShardPlan:
         parts = [torch.empty_like(latents_local) for _ in range(self.t_ways)]
         dist.all_gather(parts, latents_local.contiguous(), group=self.t_group)
         return torch.cat(parts, dim=1)
+
+
+class PeerKV:
+    """Gathered K,V buffers of a frame group in symmetric (peer-mapped) memory.
+
+    Instead of `GEMM -> all_gather`, the K,V projection GEMM of every rank stores its
+    output tiles directly into slot `t_rank` of EVERY peer's buffer (fused epilogue
+    scatter over NVLink, `dwm_linear_args.peer_out`).  Two buffers alternate between
+    consecutive temporal blocks so one group barrier per block is enough: a rank can only
+    start writing buffer b of block k+1 after every peer passed the barrier of block k,
+    i.e. finished reading buffer b in block k-1."""
+
+    def __init__(self, plan: ShardPlan, rows_local: int, width: int, dtype, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.plan = plan
+        self.rows_local, self.width = rows_local, width
+        self.bufs, self.handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty(plan.t_ways * rows_local, width, dtype=dtype,
+                               device=device)
+            self.bufs.append(t)
+            self.handles.append(symm_mem.rendezvous(t, plan.t_group))
+        self.elem = torch.empty((), dtype=dtype).element_size()
+        self.turn = 0
+
+    def next(self):
+        """(local gathered buffer, local slot view, peer slot pointers, handle)."""
+        b = self.turn
+        self.turn ^= 1
+        buf, hdl = self.bufs[b], self.handles[b]
+        r = self.plan.t_rank
+        off = r * self.rows_local * self.width * self.elem
+        slot = buf[r * self.rows_local:(r + 1) * self.rows_local]
+        peers = [int(hdl.buffer_ptrs[q]) + off for q in range(self.plan.t_ways)
+                 if q != r]
+        return buf, slot, peers, hdl

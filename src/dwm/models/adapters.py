@@ -5,9 +5,10 @@ blocks of diffusers.models.adapter (AdapterBlock / AdapterResnetBlock).
 The adapter does not depend on the latents or the timestep, yet the reference
 re-runs it inside every denoising forward (crossview_temporal_dit.py:459-462).  Here
 it is evaluated ONCE per condition set by the model's condition cache and its
-residuals are kept in token layout.  Its 1x1 convolutions run on the tcgen05 GEMM;
-the 3x3 convolutions are lowered to the same GEMM through an im2col gather
-(K = 9*C), so no cuDNN kernel is involved.
+residuals are kept in token layout.  Its 1x1 convolutions run on the tcgen05 GEMM,
+its 3x3 convolutions on the im2col-free tcgen05 convolution (`dwm_b200_conv`, taps
+iterated inside the MMA loop over the channels-last feature map); no cuDNN kernel is
+involved.
 """
 from typing import Optional
 
@@ -34,16 +35,6 @@ class AdapterBlock(torch.nn.Module):
             if in_channels != out_channels else None
         self.resnets = torch.nn.Sequential(
             *[AdapterResnetBlock(out_channels) for _ in range(num_res_blocks)])
-
-
-def _im2col3x3(x_tok, n, h, w):
-    """x_tok: 16-bit [n*h*w, C] (NHWC tokens) -> [n*h*w, 9*C], column = tap*C + c with
-    tap = ky*3+kx, zero padding 1.  Pure data movement (gather)."""
-    c = x_tok.shape[1]
-    x = x_tok.view(n, h, w, c)
-    xp = torch.nn.functional.pad(x, (0, 0, 1, 1, 1, 1))
-    cols = [xp[:, ky:ky + h, kx:kx + w, :] for ky in range(3) for kx in range(3)]
-    return torch.cat(cols, dim=-1).reshape(n * h * w, 9 * c)
 
 
 class ImageAdapter(torch.nn.Module):
@@ -128,14 +119,12 @@ class ImageAdapter(torch.nn.Module):
                     a, wgt, conv.bias.detach().float().contiguous(),
                     epilogue=_lib.EPI_F32)
             for res in block.resnets:
-                cols = _im2col3x3(tok32.to(dtype), n, h, w)
                 c1 = res.block1
-                # Conv2d weight [O, C, 3, 3] -> [O, tap*C + c]
-                w1 = c1.weight.detach().permute(0, 2, 3, 1)\
-                    .reshape(c1.out_channels, -1).to(dtype).contiguous()
-                hmid = _ops.linear(
-                    cols, w1, c1.bias.detach().float().contiguous(),
-                    act=_lib.ACT_RELU)
+                x5 = tok32.to(dtype).view(n, 1, h, w, -1)      # channels-last map
+                hmid = _ops.conv(
+                    x5, _ops.pack_conv_weight(c1.weight, dtype),
+                    c1.bias.detach().float().contiguous(), kernel=(1, 3, 3),
+                    epilogue=_lib.EPI_STORE, act=_lib.ACT_RELU)
                 tok32 = self._conv1x1(hmid, res.block2, dtype,
                                       epilogue=_lib.EPI_RESID, resid=tok32)
             if zero_conv is not None:

@@ -538,27 +538,41 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         rows = B * T_loc * V * S
         dt, dev = ws["a16"].dtype, ws["a16"].device
         if "kv_loc" not in ws:
-            ws["kv_loc"] = torch.empty(rows, 2 * D, device=dev, dtype=dt)
-            ws["kv_all"] = torch.empty(plan.t_ways * rows, 2 * D, device=dev, dtype=dt)
             ws["q_loc"] = torch.empty(rows, D, device=dev, dtype=dt)
-        kv_loc, kv_all, q_loc = ws["kv_loc"], ws["kv_all"], ws["q_loc"]
+            ws["peer_kv"] = None
+            if plan.use_peer_scatter:
+                from opendwm_b200.sharding import PeerKV
+                ws["peer_kv"] = PeerKV(plan, rows, 2 * D, dt, dev)
+                ws["kv_loc"] = True
+            else:
+                ws["kv_loc"] = torch.empty(rows, 2 * D, device=dev, dtype=dt)
+                ws["kv_all"] = torch.empty(plan.t_ways * rows, 2 * D, device=dev,
+                                           dtype=dt)
+        q_loc, peer_kv = ws["q_loc"], ws["peer_kv"]
         eps = 1e-5
 
+        def project(p, a16, w, b, nw, out, peer_out=None):
+            if p["qk_norm"]:
+                _ops.linear(a16, w, b, epilogue=_lib.EPI_QKNORM, out=out,
+                            q_norm_weight=nw, qk_region=D, qk_norm_regions=1,
+                            eps=eps, peer_out=peer_out)
+            else:
+                _ops.linear(a16, w, b, out=out, peer_out=peer_out)
+
         def qkv_attend(p, a16, out):
-            if p["qk_norm"]:
-                _ops.linear(a16, p["kv_w"], p["kv_b"], epilogue=_lib.EPI_QKNORM,
-                            out=kv_loc, q_norm_weight=p["nk"], qk_region=D,
-                            qk_norm_regions=1, eps=eps)
+            if peer_kv is not None:
+                # fused: the K,V GEMM epilogue scatters its tiles into every peer's
+                # gathered buffer over NVLink; one group barrier publishes them
+                kv_all, slot, peers, hdl = peer_kv.next()
+                project(p, a16, p["kv_w"], p["kv_b"], p.get("nk"), slot, peers)
+                project(p, a16, p["q_w"], p["q_b"], p.get("nq"), q_loc)
+                hdl.barrier(channel=0)
             else:
-                _ops.linear(a16, p["kv_w"], p["kv_b"], out=kv_loc)
-            work = plan.gather_frames_kv(kv_loc, kv_all, async_op=True)
-            if p["qk_norm"]:
-                _ops.linear(a16, p["q_w"], p["q_b"], epilogue=_lib.EPI_QKNORM,
-                            out=q_loc, q_norm_weight=p["nq"], qk_region=D,
-                            qk_norm_regions=1, eps=eps)
-            else:
-                _ops.linear(a16, p["q_w"], p["q_b"], out=q_loc)
-            work.wait()
+                kv_loc, kv_all = ws["kv_loc"], ws["kv_all"]
+                project(p, a16, p["kv_w"], p["kv_b"], p.get("nk"), kv_loc)
+                work = plan.gather_frames_kv(kv_loc, kv_all, async_op=True)
+                project(p, a16, p["q_w"], p["q_b"], p.get("nq"), q_loc)
+                work.wait()
             _ops.attention(
                 q_loc, out, D=D, heads=heads, group_dims=[B, V * S],
                 group_strides=[T_loc * V * S, 1], seq=T_loc, inner=1,

@@ -237,6 +237,17 @@ class CrossviewTemporalSD:
         self.text_encoders = self.tokenizers = "pre-encoded"
         self.vae = common_config.get("vae_instance")
         self.is_temporal_vae = bool(common_config.get("vae_is_temporal", False))
+        vae_name = common_config.get("vae")
+        vae_path = common_config.get(
+            "vae_pretrained_model_name_or_path", pretrained_model_name_or_path)
+        if self.vae is None and vae_name is not None and vae_path is not None and \
+                vae_name.endswith("AutoencoderKLCogVideoX"):
+            from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
+            self.vae = AutoencoderKLCogVideoX.from_pretrained(
+                vae_path, subfolder="vae").to(self.device)
+        if self.vae is not None and \
+                type(self.vae).__name__ == "AutoencoderKLCogVideoX":
+            self.is_temporal_vae = True
 
         if not isinstance(self.model, _compat.SD3Transformer2DModelMarker):
             raise NotImplementedError(
@@ -346,6 +357,98 @@ class CrossviewTemporalSD:
         return self.vae.decode(
             latents.to(dtype=self.vae.dtype) / self.vae.config.scaling_factor +
             shift, return_dict=False)[0]
+
+    @staticmethod
+    def postprocess(image_tensor, output_type="pt"):
+        """diffusers VaeImageProcessor.postprocess for output_type "pt"/"latent":
+        (x / 2 + 0.5).clamp(0, 1)."""
+        if output_type not in ("pt", "latent"):
+            raise NotImplementedError(
+                "output_type {} needs PIL/numpy post-processing (outside the hot "
+                "path); use \"pt\"".format(output_type))
+        if output_type == "latent":
+            return image_tensor
+        return (image_tensor / 2 + 0.5).clamp(0, 1)
+
+    @torch.no_grad()
+    def inference_pipeline(self, latent_shape, batch, output_type,
+                           image_latents=None, reference_frame_count: int = 0,
+                           start_timestep: int = 0, stop_timestep=None,
+                           take_time: int = 0):
+        """Full-sequence (or diffusion-forcing) denoising of one window followed by the
+        VAE decode — reference src/dwm/pipelines/ctsd.py:1439-1654 (the depth preview
+        branch is dropped with the depth net, SURVEY.md §2 #14)."""
+        df_mode = self.common_config.get("frame_prediction_style") == \
+            "diffusion_forcing"
+        steps = self.inference_config["inference_steps"]
+        B, T, V = latent_shape[:3]
+        if df_mode:
+            clear = self.inference_config.get("clear_reference_frame_count", 0)
+            assert steps % (T - clear) == 0
+            spi = steps // (T - clear)
+        self.test_scheduler.set_timesteps(steps, self.device)
+        self._step_cache = {}
+        if df_mode and image_latents is not None:
+            latents = image_latents.to(self.device, torch.float32).clone()
+        else:
+            latents = torch.randn(tuple(latent_shape), generator=self.generator)\
+                .to(self.device) * getattr(self.test_scheduler, "init_noise_sigma", 1)
+        latents = latents.float().contiguous()
+        conditions = CrossviewTemporalSD.get_conditions(
+            self.model, self.text_encoders, self.tokenizers, self.common_config,
+            latent_shape, batch, self.device, self.model_dtype,
+            do_classifier_free_guidance="guidance_scale" in self.inference_config,
+            latents_shape=latents.shape)
+        stop_timestep = steps if stop_timestep is None else stop_timestep
+        ts_table = self.test_scheduler.timesteps.to(self.device).float()
+        inject = (not df_mode) and image_latents is not None and \
+            reference_frame_count > 0
+        for i in range(start_timestep, stop_timestep):
+            if df_mode:
+                idx, timesteps, in_range = self._df_step_tensors(
+                    i, T, spi, take_time, B, V)
+            else:
+                idx = torch.full((B, T, V), i, dtype=torch.int32, device=self.device)
+                timesteps = ts_table[i].expand(B, T, V).contiguous()
+                in_range = None
+            if inject:
+                # reference frames enter clean at timestep 0 and are restored after
+                # the update, which reproduces the reference's per-step re-injection
+                ref = image_latents[:, :reference_frame_count].to(latents)
+                latents[:, :reference_frame_count] = ref
+                timesteps = timesteps.clone()
+                timesteps[:, :reference_frame_count] = 0
+            self.denoise_step(latents, conditions, idx, timesteps, in_range)
+        if df_mode:
+            cur = latents[:, take_time].flatten(0, 1)
+            if self.is_temporal_vae and self.vae is not None:
+                cur = torch.cat([cur[:, :, None], cur[:, :, None] * 0], dim=2)
+                image_tensor = self.decode_latents(cur).chunk(2, dim=2)[0]
+                image_tensor = image_tensor.permute(0, 2, 1, 3, 4).flatten(0, 1)
+            else:
+                image_tensor = self.decode_latents(cur)
+        else:
+            if image_latents is not None:
+                latents = torch.cat([
+                    image_latents[:, :reference_frame_count].to(latents),
+                    latents[:, reference_frame_count:]], 1)
+            split = self.common_config.get("memory_efficient_batch", -1)
+            if self.is_temporal_vae and self.vae is not None:
+                # "b t v c h w -> (b v) c t h w"
+                cur = latents.permute(0, 2, 3, 1, 4, 5).flatten(0, 1)
+                image_tensor = dwm.functional.memory_efficient_split_call(
+                    self, cur, lambda blk, t: blk.decode_latents(t), split)
+                # "(b v) c t h w -> (b t v) c h w"
+                Tn = image_tensor.shape[2]
+                image_tensor = image_tensor.view(B, V, -1, Tn, *image_tensor.shape[-2:])\
+                    .permute(0, 3, 1, 2, 4, 5).flatten(0, 2)
+            else:
+                image_tensor = dwm.functional.memory_efficient_split_call(
+                    self, latents.flatten(0, 2),
+                    lambda blk, t: blk.decode_latents(t), split)
+        images = image_tensor if self.vae is None else \
+            CrossviewTemporalSD.postprocess(image_tensor, output_type)
+        return {"images": images, "latents": latents}
 
 
 class StreamingCrossviewTemporalSD(CrossviewTemporalSD):

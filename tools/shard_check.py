@@ -63,7 +63,7 @@ def main():
                               in_range[fs].contiguous())
         return lat if plan is None else plan.gather_latents(lat)
 
-    plan = ShardPlan(world, rank, T, cfg=True)
+    plan = ShardPlan(world, rank, T, cfg=os.environ.get("SHARD_CFG", "1") != "0")
     sharded = run(plan)
     ref = run(None)
     err = ((sharded - ref).abs().max() / ref.abs().max()).item()
@@ -71,8 +71,9 @@ def main():
     t = torch.tensor([err], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print("shard_check world=%d plan=%s max rel err vs unsharded = %.3e (latents moved %.3f)"
-              % (world, plan.parallelism, t.item(), moved))
+        print("shard_check world=%d plan=%s peer_scatter=%s max rel err vs unsharded = %.3e "
+              "(latents moved %.3f)" % (world, plan.parallelism, plan.use_peer_scatter and plan.t_ways > 1,
+                                        t.item(), moved))
     dist.destroy_process_group()
     sys.exit(0 if t.item() < 2e-3 and moved > 1e-3 else 1)
 
