@@ -363,13 +363,30 @@ def run_native(args):
 
 
 # ----------------------------------------------------------------------------- CPU arms
+def _host_cores():
+    """Cores this process may actually run on (cpuset / affinity aware), capped at 64:
+    oversubscribing a cgroup-limited container makes the CPU arm slower, not faster."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:   # cgroup v2 CPU quota
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_baseline(budget_s=20.0):
     """Oracle (fp32 restatement of the reference) on the host cores: one dual
     JointTransformerBlock + one VTSelfAttentionBlock at north-star width on a bounded
     number of view-frame items; steps/s extrapolated by FLOPs (all cost is per item)."""
     from oracle import d31, ctsd as octsd
     from tools import flops as fl
-    cores = os.cpu_count() or 1
+    cores = _host_cores()
     torch.set_num_threads(cores)
     D, S, L, items = 1536, 448, 154, 2
     torch.manual_seed(0)
@@ -407,7 +424,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ctsd as octsd
-    cores = os.cpu_count() or 1
+    cores = _host_cores()
     torch.set_num_threads(cores)
     cfg = load_config(args.small)
     B, T, V, C, H, W = cfg["latent_shape"]
