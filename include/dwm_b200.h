@@ -84,7 +84,7 @@ typedef struct dwm_linear_args {
   /* RESID */
   const float* resid;   /* fp32 [*, ldr] or NULL */
   int64_t ldr;
-  int64_t resid_row_mod; /* rr(m) = resid_row_mod ? m % resid_row_mod : m */
+  int64_t resid_row_mod; /* rr(m) = m % resid_row_mod if > 0; m if 0; item(m) if < 0 */
   const float* gate;    /* fp32 [items, gate_ld] or NULL */
   int64_t gate_ld;
   const float* blend_x; /* fp32 [M, ldx] or NULL */
@@ -243,7 +243,7 @@ int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int
  *   weight 16-bit [kt*kh*kw, c_out, c_in] (tap-major: tap = (dt*kh + dh)*kw + dw)
  *   out    rows = nb*(tp-kt+1)*h*w pixels, c_out columns (channels-last), pitch ldo
  * spatial zero padding kh/2, kw/2; no implicit temporal padding.  c_out must be a multiple
- * of 256, or exactly 128, 64 or 32 (pad the weight rows).  Epilogues: DWM_EPI_STORE (16-bit,
+ * of 32 (pad the weight rows); tiles of 256 / 128 / 64 / 32 output channels.  Epilogues: DWM_EPI_STORE (16-bit,
  * bias + act), DWM_EPI_F32, DWM_EPI_RESID (fp32: acc + bias + resid).
  * Replaces diffusers CogVideoXCausalConv3d / CogVideoXUpsample3D.conv inside
  * AutoencoderKLCogVideoX.decode (called at ctsd.py:1634-1640, 1615-1617) and the
@@ -262,6 +262,10 @@ typedef struct dwm_conv_args {
   int64_t ldo;
   const float* resid;
   int64_t ldr;
+  /* resid_per_item != 0: `resid` holds ONE row per item of rows_per_item consecutive output
+   * pixels (ResnetBlock2D's `+ time_emb_proj(silu(temb))[:, :, None, None]`). */
+  int resid_per_item;
+  int64_t rows_per_item;
 } dwm_conv_args;
 
 int dwm_b200_conv(const dwm_conv_args* args, dwm_stream_t stream);

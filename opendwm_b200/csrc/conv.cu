@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       const uint32_t taddr = tmem_base + as * CBN + (static_cast<uint32_t>(quarter * 32) << 16);
       TileGeom tg;
       tg.bw = g.bw; tg.rows = g.bw * g.bh; tg.w_lim = g.w - w0; tg.h_lim = g.h - h0; tg.img_w = g.w;
+      tg.tile_cols = CBN;
       const int m_base = ((nb * g.t_out + t) * g.h + h0) * g.w + w0;
       drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256, m_base, quarter * 32, 0, n_blk * CBN, g.c_out, p,
                          lane, (warp - 2) >> 2, tg);
@@ -196,6 +197,8 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
   EpiParams p = {};
   p.out = a->out; p.ldo = a->ldo; p.bias = a->bias; p.act = a->act;
   p.resid = a->resid; p.ldr = a->ldr;
+  p.resid_row_mod = a->resid_per_item ? -1 : 0;
+  p.rows_per_item = a->rows_per_item;
   p.norm_regions = 2;
   p.n_peers = 0;
 
@@ -218,10 +221,10 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
 template <typename T, int EPI>
 static int conv_pick_bn(const dwm_conv_args* a, cudaStream_t s) {
   if (a->c_out % 256 == 0) return launch_conv<T, EPI, 256>(a, s);
-  if (a->c_out == 128) return launch_conv<T, EPI, 128>(a, s);
-  if (a->c_out == 64) return launch_conv<T, EPI, 64>(a, s);
-  if (a->c_out == 32) return launch_conv<T, EPI, 32>(a, s);
-  set_last_error("dwm_b200_conv: C_out must be a multiple of 256, or 128 / 64 / 32 (pad); got %lld", (long long)a->c_out);
+  if (a->c_out % 128 == 0) return launch_conv<T, EPI, 128>(a, s);
+  if (a->c_out % 64 == 0) return launch_conv<T, EPI, 64>(a, s);
+  if (a->c_out % 32 == 0) return launch_conv<T, EPI, 32>(a, s);
+  set_last_error("dwm_b200_conv: C_out must be a multiple of 32 (pad the weight rows); got %lld", (long long)a->c_out);
   return -1;
 }
 

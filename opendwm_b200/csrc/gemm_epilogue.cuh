@@ -26,7 +26,7 @@ struct EpiParams {
   float eps;
   int norm_regions;
   const float* resid;
-  long long ldr, resid_row_mod;
+  long long ldr, resid_row_mod;   // resid_row_mod < 0: one residual row per ITEM (m / rows_per_item)
   const float* gate;
   long long gate_ld;
   const float* blend_x;
@@ -79,12 +79,13 @@ struct TileGeom {
   int w_lim;   // img_w - w0
   int h_lim;   // img_h - h0
   int img_w;
+  int tile_cols;   // accumulator columns of this tile (0 => BN)
 };
 
 template <typename T, int EPI>
 __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_base, int row0, int M,
                                            int n_tile0, int N, const EpiParams& p, int lane,
-                                           int half, const TileGeom geom = TileGeom{0, 0, 0, 0, 0}) {
+                                           int half, const TileGeom geom = TileGeom{0, 0, 0, 0, 0, 0}) {
   constexpr bool kOut16 = (EPI == DWM_EPI_STORE || EPI == DWM_EPI_GEGLU || EPI == DWM_EPI_QKNORM);
   const int rs = lane >> 3;  // phase-2: row within a group of 4
   const int c4 = lane & 7;   // phase-2: float4 column within the 32-col chunk
@@ -117,7 +118,8 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_ba
       orow[it] = o;
       if (EPI == DWM_EPI_RESID) {
         item[it] = rpi > 0 ? m / rpi : 0;
-        rrow[it] = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod) : m;
+        rrow[it] = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod)
+                   : (p.resid_row_mod < 0 ? item[it] : m);
         alpha[it] = p.blend_x ? __ldg(p.alpha + (p.rows_per_batch > 0 ? m / static_cast<int>(p.rows_per_batch) : 0)) : 0.f;
       }
     } else {
@@ -192,7 +194,8 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_ba
 
   if constexpr (EPI == DWM_EPI_STORE || EPI == DWM_EPI_F32 || EPI == DWM_EPI_RESID) {
 #pragma unroll 1
-    for (int c = half; c < BN / 32; c += 2) {
+    const int ncols = geom.tile_cols > 0 ? geom.tile_cols : BN;
+    for (int c = half; c * 32 < ncols; c += 2) {
       const int n0 = n_tile0 + c * 32;
       if (n0 >= N) break;
       prefetch32(n0);
@@ -310,9 +313,11 @@ __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& p, int m, i
       const int cols = (N - n0) < (BN / 2) ? (N - n0) : (BN / 2);
       const uint32_t bytes = static_cast<uint32_t>(cols) * 4u;
       if (p.resid) {
-        const long long rr = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod) : m;
-        const float* src = p.resid + rr * p.ldr + n0;
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        if (p.resid_row_mod >= 0) {
+          const long long rr = p.resid_row_mod > 0 ? m % static_cast<int>(p.resid_row_mod) : m;
+          const float* src = p.resid + rr * p.ldr + n0;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+        }
       }
       if (p.blend_x) {
         const float* src = p.blend_x + static_cast<long long>(m) * p.ldx + n0;

@@ -84,6 +84,7 @@ class ConvArgs(ctypes.Structure):
         ("bias", _p), ("dtype", ctypes.c_int), ("epilogue", ctypes.c_int),
         ("act", ctypes.c_int),
         ("out", _p), ("ldo", _i64), ("resid", _p), ("ldr", _i64),
+        ("resid_per_item", ctypes.c_int), ("rows_per_item", _i64),
     ]
 
 

@@ -346,7 +346,7 @@ def pack_conv_weight(weight: torch.Tensor, dtype, pad_out_to=None, pad_in_to=Non
 
 
 def conv(x, weight, bias=None, *, kernel, epilogue=_l.EPI_F32, act=_l.ACT_NONE,
-         out=None, resid=None):
+         out=None, resid=None, resid_rows_per_item=0):
     """x: 16-bit channels-last [nb, tp, h, w, c_in]; weight: tap-major
     [kt*kh*kw, c_out, c_in]; returns [nb*(tp-kt+1)*h*w, c_out]."""
     if x.dim() != 5 or not x.is_contiguous() or not weight.is_contiguous():
@@ -374,6 +374,8 @@ def conv(x, weight, bias=None, *, kernel, epilogue=_l.EPI_F32, act=_l.ACT_NONE,
     if resid is not None:
         _rows2d(_f32(resid, "resid"), "resid")
         a.resid, a.ldr = resid.data_ptr(), resid.stride(0)
+        if resid_rows_per_item:
+            a.resid_per_item, a.rows_per_item = 1, resid_rows_per_item
     _l.check(_l.load().dwm_b200_conv(ctypes.byref(a), _stream()), "dwm_b200_conv")
     return out
 

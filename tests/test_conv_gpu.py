@@ -47,6 +47,9 @@ def test_causal_conv3d_3x3x3(dtype):
     (1, 2, 5, 9, 16, 32, (3, 3, 3)),        # tiny ragged, C_in padded... c_out 32
     (1, 1, 7, 130, 72, 3, (1, 3, 3)),       # conv_out-like: C_out 3 padded to 32
     (3, 1, 4, 4, 64, 128, (1, 1, 1)),       # 1x1x1
+    (2, 1, 8, 14, 64, 320, (1, 3, 3)),      # UNet widths: 5 tiles of 64
+    (1, 1, 8, 14, 320, 640, (1, 3, 3)),     # 5 tiles of 128, C_in 320 = 5 k-blocks
+    (1, 1, 4, 7, 128, 1280, (1, 3, 3)),     # 5 tiles of 256
 ])
 def test_shapes(shape):
     err = _case(*shape, torch.bfloat16)
@@ -56,3 +59,20 @@ def test_shapes(shape):
 def test_epilogues():
     assert _case(1, 2, 16, 56, 128, 256, (3, 3, 3), torch.bfloat16, "resid") < 1e-3
     assert _case(1, 2, 16, 56, 128, 128, (3, 3, 3), torch.bfloat16, "store") < 8e-3
+
+
+def test_per_item_residual():
+    """conv + bias + one residual row per item (ResnetBlock2D temb add)."""
+    from opendwm_b200 import ops, lib
+    nb, h, w, cin, cout = 3, 8, 14, 64, 128
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(nb, 1, h, w, cin, generator=g).bfloat16().cuda()
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * 0.05).bfloat16().cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    temb = torch.randn(nb, cout, generator=g).cuda()
+    y = ops.conv(x, ops.pack_conv_weight(wt, torch.bfloat16), b, kernel=(1, 3, 3),
+                 epilogue=lib.EPI_RESID, resid=temb, resid_rows_per_item=h * w)
+    ref = torch.nn.functional.conv2d(x[:, 0].permute(0, 3, 1, 2).float(), wt.float(), b, padding=1)
+    ref = ref + temb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, cout)
+    assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-3
