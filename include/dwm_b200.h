@@ -266,6 +266,12 @@ typedef struct dwm_conv_args {
    * pixels (ResnetBlock2D's `+ time_emb_proj(silu(temb))[:, :, None, None]`). */
   int resid_per_item;
   int64_t rows_per_item;
+  /* optional AlphaBlender after the residual (DWM_EPI_RESID):
+   * out = alpha[b] * blend_x + (1 - alpha[b]) * (acc + bias + resid), b = row / rows_per_batch */
+  const float* blend_x;
+  int64_t ldx;
+  const float* alpha;
+  int64_t rows_per_batch;
 } dwm_conv_args;
 
 int dwm_b200_conv(const dwm_conv_args* args, dwm_stream_t stream);
@@ -291,6 +297,27 @@ int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, int64_t H, 
  * [nb, T', 2H, 2W, C]. */
 int dwm_b200_upsample_nearest(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
                               int compress_time, void* out, int dtype, dwm_stream_t stream);
+
+/* out[i] = s0[i / inner] * x[i] + s1[i / inner] * y[i]: DDPMScheduler.add_noise /
+ * get_velocity with per-(b,t,v) coefficients (temporal_independent.py:8-45). */
+int dwm_b200_lincomb2(const float* x, const float* y, const float* s0, const float* s1, int64_t n,
+                      int64_t inner, float* out, dwm_stream_t stream);
+
+/* y += a * x over n fp32 elements (adapter residual adds of the UNet,
+ * crossview_temporal_unet.py:729-731, 759-761). */
+int dwm_b200_axpy(const float* x, float* y, int64_t n, float a, dwm_stream_t stream);
+
+/* Fused CFG combine + DDIM update (eta = 0) with per-(b,t,v) INT32 timesteps
+ * (reference src/dwm/schedulers/temporal_independent.py:67-170 + ctsd.py:1548-1575):
+ *   pred     fp32 [cfg * n_items * inner] (uncond half first), latent layout
+ *   latents  fp32 [n_items * inner] in/out;  timesteps int32 [n_items]
+ *   prev_t = t - step_ratio; alpha_prev = alphas_cumprod[prev_t] or final_alpha_cumprod (< 0)
+ *   prediction_type: 0 epsilon, 1 sample, 2 v_prediction. */
+int dwm_b200_cfg_ddim_step(const float* pred, int cfg, float guidance_scale, int64_t n_items,
+                           int64_t inner, const int32_t* timesteps, int step_ratio,
+                           const float* alphas_cumprod, int n_alphas, float final_alpha_cumprod,
+                           int prediction_type, float* latents, int round_dtype,
+                           dwm_stream_t stream);
 
 #ifdef __cplusplus
 }

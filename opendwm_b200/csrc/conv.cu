@@ -199,6 +199,7 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
   p.resid = a->resid; p.ldr = a->ldr;
   p.resid_row_mod = a->resid_per_item ? -1 : 0;
   p.rows_per_item = a->rows_per_item;
+  p.blend_x = a->blend_x; p.ldx = a->ldx; p.alpha = a->alpha; p.rows_per_batch = a->rows_per_batch;
   p.norm_regions = 2;
   p.n_peers = 0;
 

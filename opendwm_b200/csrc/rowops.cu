@@ -261,9 +261,104 @@ __global__ void euler_idx_kernel(const float* __restrict__ v, float* __restrict_
   x[i] = nv;
 }
 
+// y[i] += a * x[i]
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    float4 yv = *reinterpret_cast<float4*>(y + i);
+    yv.x += a * xv.x; yv.y += a * xv.y; yv.z += a * xv.z; yv.w += a * xv.w;
+    *reinterpret_cast<float4*>(y + i) = yv;
+  } else {
+    for (long long k = i; k < n; ++k) y[k] += a * x[k];
+  }
+}
+
+// Fused CFG combine + DDIM update (eta = 0) with per-(b,t,v) timesteps:
+//   pred: fp32 [cfg*B, T, V, C, H, W] (uncond half first);  lat (in/out): fp32 [B, T, V, C, H, W]
+//   ts: int32 [B, T, V] current timesteps; prev = ts - step_ratio; alphas: fp32 [num_train]
+__global__ void cfg_ddim_kernel(const float* __restrict__ pred, int cfg, float gs, long long per_b,
+                                long long inner, long long total, const int* __restrict__ ts, int step_ratio,
+                                const float* __restrict__ alphas, float final_alpha, int pred_type,
+                                float* __restrict__ lat, int round_dtype) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float v = pred[i];
+  if (cfg == 2) {
+    const float vc = pred[i + total];
+    v = v + gs * (vc - v);
+  }
+  const int t = ts[i / inner];
+  const int tp = t - step_ratio;
+  const float a_t = alphas[t];
+  const float a_p = tp >= 0 ? alphas[tp] : final_alpha;
+  const float b_t = 1.0f - a_t;
+  const float x = lat[i];
+  float x0, eps;
+  if (pred_type == 0) {          // epsilon
+    x0 = (x - sqrtf(b_t) * v) / sqrtf(a_t);
+    eps = v;
+  } else if (pred_type == 1) {   // sample
+    x0 = v;
+    eps = (x - sqrtf(a_t) * x0) / sqrtf(b_t);
+  } else {                       // v_prediction
+    x0 = sqrtf(a_t) * x - sqrtf(b_t) * v;
+    eps = sqrtf(a_t) * v + sqrtf(b_t) * x;
+  }
+  float nv = sqrtf(a_p) * x0 + sqrtf(1.0f - a_p) * eps;
+  if (round_dtype == DWM_BF16) nv = __bfloat162float(__float2bfloat16_rn(nv));
+  else if (round_dtype == DWM_F16) nv = __half2float(__float2half_rn(nv));
+  lat[i] = nv;
+  (void)per_b;
+}
+
+// out[i] = s0[i / inner] * x[i] + s1[i / inner] * y[i]
+__global__ void lincomb2_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                const float* __restrict__ s0, const float* __restrict__ s1, long long n,
+                                long long inner, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long it = i / inner;
+  out[i] = s0[it] * x[i] + s1[it] * y[i];
+}
+
 }  // namespace dwm
 
 using namespace dwm;
+
+extern "C" int dwm_b200_lincomb2(const float* x, const float* y, const float* s0, const float* s1,
+                                 int64_t n, int64_t inner, float* out, dwm_stream_t stream) {
+  DWM_REQUIRE(x && y && s0 && s1 && out && n > 0 && inner > 0 && n % inner == 0, "dwm_b200_lincomb2: bad arguments");
+  const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+  lincomb2_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, s0, s1, n, inner, out);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_axpy(const float* x, float* y, int64_t n, float a, dwm_stream_t stream) {
+  DWM_REQUIRE(x && y && n > 0, "dwm_b200_axpy: bad arguments");
+  const unsigned grid = static_cast<unsigned>((n / 4 + 1 + 255) / 256);
+  axpy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n, a);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_cfg_ddim_step(const float* pred, int cfg, float guidance_scale, int64_t n_items,
+                                      int64_t inner, const int32_t* timesteps, int step_ratio,
+                                      const float* alphas_cumprod, int n_alphas, float final_alpha_cumprod,
+                                      int prediction_type, float* latents, int round_dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(pred && timesteps && alphas_cumprod && latents, "dwm_b200_cfg_ddim_step: null pointer");
+  DWM_REQUIRE((cfg == 1 || cfg == 2) && n_items > 0 && inner > 0 && n_alphas > 0 && prediction_type >= 0 &&
+                  prediction_type <= 2,
+              "dwm_b200_cfg_ddim_step: bad arguments");
+  const long long total = n_items * inner;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  cfg_ddim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      pred, cfg, guidance_scale, 0, inner, total, timesteps, step_ratio, alphas_cumprod, final_alpha_cumprod,
+      prediction_type, latents, round_dtype);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int dwm_b200_euler_step_by_indices(const float* model_output, float* sample, int64_t n,
                                               int64_t inner, const int32_t* idx, const float* sigmas,

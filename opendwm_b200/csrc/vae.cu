@@ -44,6 +44,39 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
+// generic variant: any C, any group size (scalar loads; UNet widths 320 / 960 / 1920 ...)
+__global__ void __launch_bounds__(256) gn_stats_generic_kernel(const float* __restrict__ x, long long pixels, int C,
+                                                               int G, long long pixels_per_block,
+                                                               double* __restrict__ sums) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  __syncthreads();
+  const int cg = C / G;
+  const long long e0 = static_cast<long long>(blockIdx.x) * pixels_per_block * C;
+  long long e1 = e0 + pixels_per_block * C;
+  if (e1 > pixels * C) e1 = pixels * C;
+  const float* base = x + static_cast<long long>(n) * pixels * C;
+  // consecutive threads read consecutive elements; accumulate runs of equal group locally
+  int cur_g = -1;
+  float a = 0.f, b = 0.f;
+  for (long long e = e0 + tid; e < e1; e += 256) {
+    const int g = static_cast<int>(e % C) / cg;
+    if (g != cur_g) {
+      if (cur_g >= 0) { atomicAdd(&s_sum[cur_g], a); atomicAdd(&s_sq[cur_g], b); }
+      cur_g = g; a = 0.f; b = 0.f;
+    }
+    const float v = base[e];
+    a += v; b += v * v;
+  }
+  if (cur_g >= 0) { atomicAdd(&s_sum[cur_g], a); atomicAdd(&s_sq[cur_g], b); }
+  __syncthreads();
+  if (tid < G) {
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2], static_cast<double>(s_sum[tid]));
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2 + 1], static_cast<double>(s_sq[tid]));
+  }
+}
+
 // ---- SpatialNorm3D / GroupNorm apply (+SiLU) -> 16-bit, written at a frame offset ----
 struct SnParams {
   const float* x; int nb, T, H, W, C, G;
@@ -66,20 +99,38 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
   const int h = static_cast<int>(r % p.H); r /= p.H;
   const int t = static_cast<int>(r % p.T);
   const int n = static_cast<int>(r / p.T);
-  const int g = (c4 * 4) / (p.C / p.G);
-  const double cnt = static_cast<double>(p.C / p.G) * p.T * p.H * p.W;
-  const double s = p.sums[(static_cast<long long>(n) * p.G + g) * 2];
-  const double ss = p.sums[(static_cast<long long>(n) * p.G + g) * 2 + 1];
-  const double mean_d = s / cnt;
-  const float mean = static_cast<float>(mean_d);
-  const float rstd = rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps);
+  const int cg = p.C / p.G;
+  const double cnt = static_cast<double>(cg) * p.T * p.H * p.W;
+  auto stats = [&](int g, float& mean, float& rstd) {
+    const double s = p.sums[(static_cast<long long>(n) * p.G + g) * 2];
+    const double ss = p.sums[(static_cast<long long>(n) * p.G + g) * 2 + 1];
+    const double mean_d = s / cnt;
+    mean = static_cast<float>(mean_d);
+    rstd = rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps);
+  };
   float4 v = reinterpret_cast<const float4*>(p.x)[i];
   const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
   const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
-  v.x = (v.x - mean) * rstd * ga.x + be.x;
-  v.y = (v.y - mean) * rstd * ga.y + be.y;
-  v.z = (v.z - mean) * rstd * ga.z + be.z;
-  v.w = (v.w - mean) * rstd * ga.w + be.w;
+  if ((cg & 3) == 0) {
+    float mean, rstd;
+    stats((c4 * 4) / cg, mean, rstd);
+    v.x = (v.x - mean) * rstd * ga.x + be.x;
+    v.y = (v.y - mean) * rstd * ga.y + be.y;
+    v.z = (v.z - mean) * rstd * ga.z + be.z;
+    v.w = (v.w - mean) * rstd * ga.w + be.w;
+  } else {   // a float4 may straddle groups (e.g. 10 or 2 channels per group): per-element statistics
+    float* ve = reinterpret_cast<float*>(&v);
+    const float* gae = reinterpret_cast<const float*>(&ga);
+    const float* bee = reinterpret_cast<const float*>(&be);
+    int g_prev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (c4 * 4 + e) / cg;
+      if (g != g_prev) { stats(g, mean, rstd); g_prev = g; }
+      ve[e] = (ve[e] - mean) * rstd * gae[e] + bee[e];
+    }
+  }
   if (p.zy) {
     // nearest-neighbour position in the latent grid; odd T > 1 treats the first frame apart
     int tz;
@@ -128,14 +179,15 @@ using namespace dwm;
 extern "C" int dwm_b200_groupnorm_stats(const float* x, int64_t nb, int64_t pixels, int C, int groups,
                                         double* sums, dwm_stream_t stream) {
   DWM_REQUIRE(x && sums && nb > 0 && pixels > 0, "dwm_b200_groupnorm_stats: bad arguments");
-  DWM_REQUIRE(C % 4 == 0 && C / 4 <= 256 && groups > 0 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 &&
-                  256 % (C / 4) == 0,
-              "dwm_b200_groupnorm_stats: need C %% (4*groups) == 0, C/4 a divisor of 256 (got C=%d, groups=%d)", C, groups);
+  DWM_REQUIRE(C % 4 == 0 && groups > 0 && groups <= 64 && C % groups == 0,
+              "dwm_b200_groupnorm_stats: need C %% 4 == 0, C %% groups == 0, groups <= 64 (got C=%d, groups=%d)", C, groups);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DWM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * nb * groups, s));
-  const long long ppb = 1024;
+  const bool fast = (C / groups) % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0;
+  const long long ppb = fast ? 1024 : 64;
   dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
-  gn_stats_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  if (fast) gn_stats_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  else gn_stats_generic_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -146,7 +198,7 @@ extern "C" int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, 
                                          int wz, int apply_silu, void* out, int64_t out_T, int64_t out_t0,
                                          int dtype, dwm_stream_t stream) {
   DWM_REQUIRE(x && sums && gamma && beta && out, "dwm_b200_spatialnorm_silu: null pointer");
-  DWM_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0, "dwm_b200_spatialnorm_silu: bad C/groups");
+  DWM_REQUIRE(C % 4 == 0 && groups > 0 && C % groups == 0, "dwm_b200_spatialnorm_silu: bad C/groups");
   DWM_REQUIRE((zy == nullptr) == (zb == nullptr), "dwm_b200_spatialnorm_silu: zy and zb go together");
   DWM_REQUIRE(out_t0 >= 0 && out_t0 + T <= out_T, "dwm_b200_spatialnorm_silu: frame window outside out buffer");
   SnParams p;

@@ -85,6 +85,7 @@ class ConvArgs(ctypes.Structure):
         ("act", ctypes.c_int),
         ("out", _p), ("ldo", _i64), ("resid", _p), ("ldr", _i64),
         ("resid_per_item", ctypes.c_int), ("rows_per_item", _i64),
+        ("blend_x", _p), ("ldx", _i64), ("alpha", _p), ("rows_per_batch", _i64),
     ]
 
 
@@ -109,6 +110,11 @@ SYMBOLS = {
         ctypes.c_int, ctypes.c_int, ctypes.c_int, _p, _p, ctypes.c_int, _p, _p,
         _p, ctypes.c_int, _p]),
     "dwm_b200_conv": (ctypes.c_int, [ctypes.POINTER(ConvArgs), _p]),
+    "dwm_b200_axpy": (ctypes.c_int, [_p, _p, _i64, ctypes.c_float, _p]),
+    "dwm_b200_lincomb2": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p]),
+    "dwm_b200_cfg_ddim_step": (ctypes.c_int, [
+        _p, ctypes.c_int, ctypes.c_float, _i64, _i64, _p, ctypes.c_int, _p,
+        ctypes.c_int, ctypes.c_float, ctypes.c_int, _p, ctypes.c_int, _p]),
     "dwm_b200_groupnorm_stats": (ctypes.c_int, [_p, _i64, _i64, ctypes.c_int,
                                                 ctypes.c_int, _p, _p]),
     "dwm_b200_spatialnorm_silu": (ctypes.c_int, [

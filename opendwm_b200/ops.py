@@ -346,7 +346,8 @@ def pack_conv_weight(weight: torch.Tensor, dtype, pad_out_to=None, pad_in_to=Non
 
 
 def conv(x, weight, bias=None, *, kernel, epilogue=_l.EPI_F32, act=_l.ACT_NONE,
-         out=None, resid=None, resid_rows_per_item=0):
+         out=None, resid=None, resid_rows_per_item=0, blend_x=None, alpha=None,
+         rows_per_batch=0):
     """x: 16-bit channels-last [nb, tp, h, w, c_in]; weight: tap-major
     [kt*kh*kw, c_out, c_in]; returns [nb*(tp-kt+1)*h*w, c_out]."""
     if x.dim() != 5 or not x.is_contiguous() or not weight.is_contiguous():
@@ -376,6 +377,10 @@ def conv(x, weight, bias=None, *, kernel, epilogue=_l.EPI_F32, act=_l.ACT_NONE,
         a.resid, a.ldr = resid.data_ptr(), resid.stride(0)
         if resid_rows_per_item:
             a.resid_per_item, a.rows_per_item = 1, resid_rows_per_item
+    if blend_x is not None:
+        _rows2d(_f32(blend_x, "blend_x"), "blend_x")
+        a.blend_x, a.ldx = blend_x.data_ptr(), blend_x.stride(0)
+        a.alpha, a.rows_per_batch = _f32(alpha, "alpha").data_ptr(), rows_per_batch
     _l.check(_l.load().dwm_b200_conv(ctypes.byref(a), _stream()), "dwm_b200_conv")
     return out
 
@@ -424,4 +429,50 @@ def upsample_nearest(x, compress_time, dtype):
     _l.check(_l.load().dwm_b200_upsample_nearest(
         x.data_ptr(), nb, T, H, W, C, int(compress_time), out.data_ptr(), _dt(out),
         _stream()), "dwm_b200_upsample_nearest")
+    return out
+
+
+def axpy(x, y, a=1.0):
+    """y += a * x (fp32, in place)."""
+    _f32(x, "x")
+    _f32(y, "y")
+    if x.numel() != y.numel() or not (x.is_contiguous() and y.is_contiguous()):
+        raise ValueError("axpy needs contiguous tensors of equal size")
+    _l.check(_l.load().dwm_b200_axpy(x.data_ptr(), y.data_ptr(), x.numel(), float(a),
+                                     _stream()), "dwm_b200_axpy")
+    return y
+
+
+def cfg_ddim_step(pred, latents, timesteps, alphas_cumprod, *, cfg, guidance_scale,
+                  step_ratio, final_alpha_cumprod, prediction_type,
+                  round_dtype=torch.float32):
+    """Fused CFG + DDIM (eta 0) update of fp32 latents [B,T,V,...] in place."""
+    _f32(pred, "pred")
+    _f32(latents, "latents")
+    _f32(alphas_cumprod, "alphas_cumprod")
+    if not (pred.is_contiguous() and latents.is_contiguous() and timesteps.is_contiguous()):
+        raise ValueError("cfg_ddim_step needs contiguous tensors")
+    if timesteps.dtype != torch.int32:
+        raise TypeError("timesteps must be int32")
+    n_items = timesteps.numel()
+    inner = latents.numel() // n_items
+    code = {"epsilon": 0, "sample": 1, "v_prediction": 2}[prediction_type]
+    _l.check(_l.load().dwm_b200_cfg_ddim_step(
+        pred.data_ptr(), cfg, float(guidance_scale), n_items, inner,
+        timesteps.data_ptr(), int(step_ratio), alphas_cumprod.data_ptr(),
+        alphas_cumprod.numel(), float(final_alpha_cumprod), code, latents.data_ptr(),
+        _code(round_dtype), _stream()), "dwm_b200_cfg_ddim_step")
+    return latents
+
+
+def lincomb2(x, y, s0, s1, out):
+    """out = s0[item] * x + s1[item] * y with one coefficient pair per item."""
+    for t, nme in ((x, "x"), (y, "y"), (s0, "s0"), (s1, "s1"), (out, "out")):
+        _f32(t, nme)
+        if not t.is_contiguous():
+            raise ValueError("lincomb2 needs contiguous tensors")
+    n = x.numel()
+    _l.check(_l.load().dwm_b200_lincomb2(
+        x.data_ptr(), y.data_ptr(), s0.data_ptr(), s1.data_ptr(), n, n // s0.numel(),
+        out.data_ptr(), _stream()), "dwm_b200_lincomb2")
     return out

@@ -416,3 +416,68 @@ def df_denoise_step(model, scheduler, latents, conditions, i, steps_per_inferenc
         df_in_schedule_range(i, T, steps_per_inference), device=latents.device)\
         .view(1, T, 1, 1, 1, 1)
     return torch.where(in_range, staging, latents), noise_pred
+
+
+# -- SD-2.1 schedulers (temporal_independent.py:8-170; diffusers DDIM/DDPM tables, A.8) -----
+
+def scaled_linear_alphas(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                           dtype=torch.float32) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class DDPMSchedulerOracle:
+    """temporal_independent.py:8-45."""
+
+    def __init__(self, **kw):
+        self.alphas_cumprod = scaled_linear_alphas(**kw)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        while timesteps.dim() < original_samples.dim():
+            timesteps = timesteps.unsqueeze(-1)
+        a = self.alphas_cumprod.to(original_samples)[timesteps.long()]
+        return a ** 0.5 * original_samples + (1 - a) ** 0.5 * noise
+
+    def get_velocity(self, sample, noise, timesteps):
+        while timesteps.dim() < sample.dim():
+            timesteps = timesteps.unsqueeze(-1)
+        a = self.alphas_cumprod.to(sample)[timesteps.long()]
+        return a ** 0.5 * noise - (1 - a) ** 0.5 * sample
+
+
+class DDIMSchedulerOracle:
+    """temporal_independent.py:48-170 with eta = 0 (leading spacing, steps_offset)."""
+
+    def __init__(self, num_train_timesteps=1000, prediction_type="v_prediction",
+                 steps_offset=1, set_alpha_to_one=False, **kw):
+        self.num_train_timesteps = num_train_timesteps
+        self.prediction_type = prediction_type
+        self.steps_offset = steps_offset
+        self.alphas_cumprod = scaled_linear_alphas(num_train_timesteps, **kw)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one \
+            else self.alphas_cumprod[0]
+
+    def set_timesteps(self, n):
+        self.num_inference_steps = n
+        ratio = self.num_train_timesteps // n
+        self.timesteps = (torch.arange(0, n) * ratio).flip(0) + self.steps_offset
+
+    def step(self, model_output, timestep, sample):
+        while timestep.dim() < sample.dim():
+            timestep = timestep.unsqueeze(-1)
+        prev = timestep - self.num_train_timesteps // self.num_inference_steps
+        ac = self.alphas_cumprod.to(sample.device)
+        a_t = ac[timestep.long()]
+        a_p = torch.where(prev >= 0, ac[prev.clamp_min(0).long()],
+                          self.final_alpha_cumprod.to(sample.device))
+        b_t = 1 - a_t
+        if self.prediction_type == "epsilon":
+            x0 = (sample - b_t ** 0.5 * model_output) / a_t ** 0.5
+            eps = model_output
+        elif self.prediction_type == "sample":
+            x0 = model_output
+            eps = (sample - a_t ** 0.5 * x0) / b_t ** 0.5
+        else:
+            x0 = a_t ** 0.5 * sample - b_t ** 0.5 * model_output
+            eps = a_t ** 0.5 * model_output + b_t ** 0.5 * sample
+        return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps

@@ -249,22 +249,37 @@ class CrossviewTemporalSD:
                 type(self.vae).__name__ == "AutoencoderKLCogVideoX":
             self.is_temporal_vae = True
 
-        if not isinstance(self.model, _compat.SD3Transformer2DModelMarker):
-            raise NotImplementedError(
-                "only the SD-3.x DiT model family is implemented in this round")
-        test_scheduler_type = dwm.common.get_class(self.inference_config.get(
-            "scheduler",
-            "dwm.schedulers.temporal_independent.FlowMatchEulerDiscreteScheduler"))
+        self.is_dit = isinstance(self.model, _compat.SD3Transformer2DModelMarker)
+        if not self.is_dit and not isinstance(
+                self.model, _compat.UNetSpatioTemporalConditionModelMarker):
+            raise Exception("Unsupported diffusion model type.")
+        default_scheduler = \
+            "dwm.schedulers.temporal_independent.FlowMatchEulerDiscreteScheduler" \
+            if self.is_dit else "dwm.schedulers.temporal_independent.DDIMScheduler"
+        name = self.inference_config.get("scheduler", default_scheduler)
+        # the reference's defaults / examples name diffusers classes; map them to mirrors
+        name = {"diffusers.DDIMScheduler":
+                "dwm.schedulers.temporal_independent.DDIMScheduler",
+                "diffusers.FlowMatchEulerDiscreteScheduler": default_scheduler}.get(
+                    name, name)
+        test_scheduler_type = dwm.common.get_class(name)
         sched_dir = None if pretrained_model_name_or_path is None else \
             os.path.join(pretrained_model_name_or_path, "scheduler")
         if sched_dir is not None and os.path.exists(
                 os.path.join(sched_dir, "scheduler_config.json")):
             self.test_scheduler = test_scheduler_type.from_pretrained(
                 pretrained_model_name_or_path, subfolder="scheduler")
-        else:
+        elif self.is_dit:
             # stable-diffusion-3.5-medium scheduler/scheduler_config.json values
             self.test_scheduler = test_scheduler_type(
                 num_train_timesteps=1000, shift=3.0)
+        else:
+            # stable-diffusion-2-1 scheduler/scheduler_config.json values
+            self.test_scheduler = test_scheduler_type(
+                num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                beta_schedule="scaled_linear", clip_sample=False,
+                set_alpha_to_one=False, steps_offset=1,
+                prediction_type="v_prediction")
 
         if resume_from is not None:
             self.model.load_state_dict(CrossviewTemporalSD.load_state(
@@ -311,6 +326,8 @@ class CrossviewTemporalSD:
         update and masked latent update.  `latents` fp32 [B,T,V,C,H,W] is updated in
         place; idx int32 [B,T,V]; timesteps fp32 [B,T,V]."""
         do_cfg = "guidance_scale" in self.inference_config
+        if not self.is_dit:
+            return self._denoise_step_unet(latents, conditions, timesteps, do_cfg)
         plan = self.sharding
         x = latents
         t = timesteps
@@ -345,6 +362,31 @@ class CrossviewTemporalSD:
             guidance_scale=self.inference_config.get("guidance_scale", 1),
             patch=self.model.patch_size, in_range=in_range,
             round_dtype=self.model_dtype)
+        return latents
+
+    def _denoise_step_unet(self, latents, conditions, timesteps, do_cfg):
+        """CTSD-2.1 step: CFG batching, UNet forward, fused CFG + DDIM (eta 0) update
+        (reference ctsd.py:1536-1575 with the in-repo DDIMScheduler.step)."""
+        x = torch.cat([latents, latents]) if do_cfg else latents
+        t = torch.cat([timesteps, timesteps]) if do_cfg else timesteps
+        out, _, _ = self.model(
+            x.to(self.model_dtype), t,
+            encoder_hidden_states=conditions["encoder_hidden_states"],
+            condition_image_tensor=conditions.get("condition_image_tensor"),
+            disable_crossview=conditions.get("disable_crossview"),
+            disable_temporal=conditions.get("disable_temporal"),
+            crossview_attention_mask=conditions.get("crossview_attention_mask"),
+            added_time_ids=conditions.get("added_time_ids"))
+        sch = self.test_scheduler
+        sch.alphas_cumprod = sch.alphas_cumprod.to(latents.device)
+        _ops.cfg_ddim_step(
+            out[0].float().contiguous(), latents,
+            timesteps.to(torch.int32).contiguous(), sch.alphas_cumprod,
+            cfg=2 if do_cfg else 1,
+            guidance_scale=self.inference_config.get("guidance_scale", 1),
+            step_ratio=sch.config.num_train_timesteps // sch.num_inference_steps,
+            final_alpha_cumprod=float(sch.final_alpha_cumprod),
+            prediction_type=sch.config.prediction_type, round_dtype=torch.float32)
         return latents
 
     def decode_latents(self, latents):
@@ -410,6 +452,8 @@ class CrossviewTemporalSD:
             else:
                 idx = torch.full((B, T, V), i, dtype=torch.int32, device=self.device)
                 timesteps = ts_table[i].expand(B, T, V).contiguous()
+                if not self.is_dit:
+                    timesteps = timesteps.round().to(torch.int32)
                 in_range = None
             if inject:
                 # reference frames enter clean at timestep 0 and are restored after

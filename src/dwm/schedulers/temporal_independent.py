@@ -112,3 +112,142 @@ def df_in_schedule_range(i: int, sequence_length: int,
                          steps_per_inference: int):
     """reference src/dwm/pipelines/ctsd.py:2083-2088."""
     return [i - j * steps_per_inference >= 0 for j in range(sequence_length)]
+
+
+def _scaled_linear_alphas(num_train_timesteps, beta_start, beta_end, beta_schedule):
+    if beta_schedule == "scaled_linear":
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                               dtype=torch.float32) ** 2
+    elif beta_schedule == "linear":
+        betas = torch.linspace(beta_start, beta_end, num_train_timesteps,
+                               dtype=torch.float32)
+    else:
+        raise NotImplementedError(beta_schedule)
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+class _SchedulerBase:
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kwargs):
+        path = pretrained_model_name_or_path
+        if subfolder:
+            path = os.path.join(path, subfolder)
+        with open(os.path.join(path, "scheduler_config.json")) as f:
+            cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+
+class DDPMScheduler(_SchedulerBase):
+    """`add_noise` / `get_velocity` with per-(b,t,v) timesteps (reference
+    src/dwm/schedulers/temporal_independent.py:8-45).  INT gather of the cumulative-alpha
+    table, then one fused `s0[item]*x + s1[item]*y` pass on the GPU."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02,
+                 beta_schedule="linear", prediction_type="epsilon", **unused):
+        self.config = _Config(num_train_timesteps=num_train_timesteps,
+                              beta_start=beta_start, beta_end=beta_end,
+                              beta_schedule=beta_schedule,
+                              prediction_type=prediction_type)
+        self.alphas_cumprod = _scaled_linear_alphas(
+            num_train_timesteps, beta_start, beta_end, beta_schedule)
+
+    def _mix(self, x, y, timesteps, sign):
+        if not x.is_cuda:
+            raise RuntimeError("scheduler kernels run on CUDA only (no CPU fallback)")
+        self.alphas_cumprod = self.alphas_cumprod.to(x.device)
+        a = self.alphas_cumprod[timesteps.to(x.device).long().flatten()]
+        s0 = (a ** 0.5).float().contiguous()
+        s1 = (sign * (1 - a) ** 0.5).float().contiguous()
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        _ops.lincomb2(x.float().contiguous(), y.float().contiguous(), s0, s1, out)
+        return out.to(x.dtype)
+
+    def add_noise(self, original_samples, noise, timesteps):
+        # sqrt(a_t) * x0 + sqrt(1 - a_t) * noise
+        return self._mix(original_samples, noise, timesteps, 1.0)
+
+    def get_velocity(self, sample, noise, timesteps):
+        # sqrt(a_t) * noise - sqrt(1 - a_t) * sample
+        return self._mix(noise, sample, timesteps, -1.0)
+
+
+@dataclass
+class DDIMSchedulerOutput:
+    prev_sample: torch.Tensor
+    pred_original_sample: torch.Tensor = None
+
+
+class DDIMScheduler(_SchedulerBase):
+    """DDIM (eta = 0) with tensor timesteps (reference
+    src/dwm/schedulers/temporal_independent.py:48-170; `set_timesteps` and the alpha
+    tables restate diffusers==0.31.0 DDIMScheduler)."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02,
+                 beta_schedule="linear", clip_sample=True, set_alpha_to_one=True,
+                 steps_offset=0, prediction_type="epsilon", thresholding=False,
+                 timestep_spacing="leading", clip_sample_range=1.0, **unused):
+        if thresholding or clip_sample:
+            raise NotImplementedError(
+                "clip_sample / thresholding are off in the SD-2.1 scheduler config")
+        self.config = _Config(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start,
+            beta_end=beta_end, beta_schedule=beta_schedule, clip_sample=clip_sample,
+            set_alpha_to_one=set_alpha_to_one, steps_offset=steps_offset,
+            prediction_type=prediction_type, timestep_spacing=timestep_spacing)
+        self.alphas_cumprod = _scaled_linear_alphas(
+            num_train_timesteps, beta_start, beta_end, beta_schedule)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one \
+            else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        n_train = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        spacing = self.config.timestep_spacing
+        if spacing == "leading":
+            ratio = n_train // num_inference_steps
+            ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1]\
+                .copy().astype(np.int64) + self.config.steps_offset
+        elif spacing == "trailing":
+            ratio = n_train / num_inference_steps
+            ts = np.round(np.arange(n_train, 0, -ratio)).astype(np.int64) - 1
+        elif spacing == "linspace":
+            ts = np.linspace(0, n_train - 1, num_inference_steps).round()[::-1]\
+                .copy().astype(np.int64)
+        else:
+            raise ValueError(spacing)
+        self.timesteps = torch.from_numpy(ts).to(device)
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0,
+             use_clipped_model_output: bool = False, generator=None,
+             variance_noise=None, return_dict: bool = True):
+        if self.num_inference_steps is None:
+            raise ValueError(
+                "Number of inference steps is 'None', you need to run "
+                "'set_timesteps' after creating the scheduler")
+        if eta != 0.0 or use_clipped_model_output:
+            raise NotImplementedError("only the deterministic DDIM update (eta = 0)")
+        if not model_output.is_cuda:
+            raise RuntimeError("scheduler kernels run on CUDA only (no CPU fallback)")
+        lead = sample.shape[:-3]
+        ts = torch.as_tensor(timestep).to(sample.device, torch.int32)
+        while ts.dim() > len(lead) and ts.shape[-1] == 1:
+            ts = ts.squeeze(-1)
+        ts = ts.expand(lead).contiguous()
+        out = sample.to(torch.float32).contiguous().clone()
+        _ops.cfg_ddim_step(
+            model_output.float().contiguous(), out, ts,
+            self.alphas_cumprod.to(sample.device), cfg=1, guidance_scale=1.0,
+            step_ratio=self.config.num_train_timesteps // self.num_inference_steps,
+            final_alpha_cumprod=float(self.final_alpha_cumprod),
+            prediction_type=self.config.prediction_type)
+        prev = out.to(sample.dtype)
+        if not return_dict:
+            return (prev, None)
+        return DDIMSchedulerOutput(prev_sample=prev)
