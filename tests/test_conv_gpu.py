@@ -16,7 +16,7 @@ def _case(nb, t_out, h, w, cin, cout, kernel, dtype, epilogue="f32", seed=0):
     ref = torch.nn.functional.conv3d(x.float(), wt.float(), b, padding=(0, kh // 2, kw // 2))
     ref = ref.permute(0, 2, 3, 4, 1).reshape(-1, cout)                              # channels-last rows
     cin_p = (cin + 7) // 8 * 8
-    cout_p = cout if (cout % 256 == 0 or cout in (128, 32)) else (32 if cout < 32 else None)
+    cout_p = (cout + 31) // 32 * 32
     xcl = torch.zeros(nb, t_out + kt - 1, h, w, cin_p, dtype=dtype, device="cuda")
     xcl[..., :cin] = x.permute(0, 2, 3, 4, 1)
     wp = ops.pack_conv_weight(wt, dtype, pad_out_to=cout_p, pad_in_to=cin_p)

@@ -44,15 +44,15 @@ def test_df_step_matches_golden():
     assert not torch.equal(lat, sample[:1])
 
 
-def _batch(T, V, cfg, L=10, seed=0):
+def _batch(T, V, cfg, L=10, seed=0, hw=(64, 96)):
     g = torch.Generator().manual_seed(seed)
     return {
         "pts": torch.zeros(1, T, V),
         "fps": torch.tensor([10.0]),
         "text_embeddings": torch.randn(1, T, V, L, cfg["joint_attention_dim"], generator=g) * 0.5,
         "pooled_text_embeddings": torch.randn(1, T, V, cfg["pooled_projection_dim"], generator=g),
-        "3dbox_images": torch.rand(1, T, V, 3, 64, 96, generator=g),
-        "hdmap_images": torch.rand(1, T, V, 3, 64, 96, generator=g),
+        "3dbox_images": torch.rand(1, T, V, 3, *hw, generator=g),
+        "hdmap_images": torch.rand(1, T, V, 3, *hw, generator=g),
         "crossview_mask": torch.ones(1, V, V, dtype=torch.bool),
         "camera_intrinsics": torch.eye(3).expand(1, T, V, 3, 3).clone(),
         "camera_transforms": torch.eye(4).expand(1, T, V, 4, 4).clone(),
@@ -102,3 +102,47 @@ def test_full_sequence_pipeline_with_temporal_vae():
     assert r["images"].shape == (1 * 9 * 3, 3, 64, 96)
     assert r["latents"].shape == (1, 3, 3, 16, 8, 12)
     assert 0 <= r["images"].min() and r["images"].max() <= 1
+
+
+def test_unet_ddim_pipeline_matches_oracle_loop():
+    """CTSD-2.1 family through the same pipeline class: CFG + UNet + DDIM (v-prediction)
+    for 3 steps against an fp32 oracle loop (oracle UNet + DDIMSchedulerOracle)."""
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    from oracle.ctsd import DDIMSchedulerOracle
+    from test_unet import UCFG, _oracle
+    o = _oracle(UCFG).cuda()
+    m = U(**UCFG, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    common = dict(COMMON, frame_prediction_style="ctsd")
+    inf = {"guidance_scale": 3.0, "inference_steps": 3}
+    pipe = CrossviewTemporalSD(None, {"generator_seed": 0}, "cuda", common, {}, inf, None, m,
+                               model_dtype=torch.float32)
+    assert not pipe.is_dit and type(pipe.test_scheduler).__name__ == "DDIMScheduler"
+    B, T, V = 1, 2, 3
+    shape = (B, T, V, 4, 16, 24)
+    batch = _batch(T, V, dict(joint_attention_dim=96, pooled_projection_dim=8), hw=(128, 192))
+    r = pipe.inference_pipeline(shape, batch, "pt")
+    assert pipe.test_scheduler.timesteps.tolist() == [667, 334, 1]
+
+    # oracle loop on the same noise and conditions
+    lat = torch.randn(shape, generator=torch.Generator().manual_seed(0)).cuda()
+    cond = CrossviewTemporalSD.get_conditions(
+        m, object(), None, common, shape, batch, "cuda", torch.float32,
+        do_classifier_free_guidance=True)
+    sch = DDIMSchedulerOracle(beta_start=0.00085, beta_end=0.012)
+    sch.set_timesteps(3)
+    with torch.no_grad():
+        for t in sch.timesteps.tolist():
+            tt = torch.full((2 * B, T, V), t, device="cuda")
+            out = o(torch.cat([lat, lat]), tt.float(),
+                    encoder_hidden_states=cond["encoder_hidden_states"],
+                    condition_image_tensor=cond["condition_image_tensor"],
+                    disable_crossview=cond["disable_crossview"],
+                    disable_temporal=cond["disable_temporal"],
+                    crossview_attention_mask=cond["crossview_attention_mask"],
+                    added_time_ids=cond["added_time_ids"])[0]
+            u, c = out.chunk(2)
+            lat = sch.step(u + 3.0 * (c - u), tt[:B], lat)
+    err = ((r["latents"] - lat).abs().max() / lat.abs().max()).item()
+    assert err < 8e-3, err
