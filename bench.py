@@ -285,6 +285,9 @@ def run_native(args):
     if rank != 0:
         torch.distributed.destroy_process_group()
         return
+    frame_latency = None
+    if world == 1 and not args.small:
+        frame_latency = decode_latency(dev, dtype, V, C, H, W, ms)
     peak_tf, peak_hbm, peak_src = peaks()
     gemm_ms = sum(p["ms"] for p in prof["linear"])
     gemm_fl = sum(p["flops"] for p in prof["linear"])
@@ -340,6 +343,8 @@ def run_native(args):
         "gpu_launches": prof["launches"],
         "clocks": clocks,
     }
+    if frame_latency is not None:
+        line["frame_latency"] = frame_latency
     if args.profile_dump:
         agg = {}
         for p_ in prof["linear"]:
@@ -360,6 +365,35 @@ def run_native(args):
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def decode_latency(dev, dtype, V, C, H, W, ms_step):
+    """Per-emitted-frame latency of the streaming loop: 3 denoise steps
+    + the 6-view temporal-VAE decode of the exiting frame exactly as
+    StreamingCrossviewTemporalSD.receive_frame issues it (frame + zero frame, reference
+    ctsd.py:1609-1621).  Untimed by the headline; reported beside it."""
+    from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
+    try:
+        torch.manual_seed(0)
+        with torch.device(dev):
+            vae = AutoencoderKLCogVideoX(compute_dtype=dtype)
+        cur = torch.randn(V, C, 1, H, W, device=dev)
+        z = torch.cat([cur, cur * 0], dim=2)
+        vae.decode(z, return_dict=False)                 # warm-up: packs weights
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            y = vae.decode(z, return_dict=False)[0]
+        e1.record()
+        torch.cuda.synchronize()
+        dec = e0.elapsed_time(e1) / 3
+        return {"ms": 3 * ms_step + dec, "decode_ms": dec, "denoise_ms": 3 * ms_step,
+                "decode_out_shape": list(y.shape),
+                "definition": "3 denoise steps (spi) + CogVideoX decode of 6 views x "
+                              "(frame, zero frame) at 256x448"}
+    except Exception as e:                               # never lose the headline line
+        return {"error": repr(e)[:200]}
 
 
 # ----------------------------------------------------------------------------- CPU arms

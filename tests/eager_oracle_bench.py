@@ -1,0 +1,64 @@
+"""Measurement only (not collected by pytest): the oracle restatement of the reference's
+PyTorch path run EAGERLY ON THE B200 in bf16 (autocast + SDPA), one north-star
+diffusion-forcing denoise step — SURVEY.md §8(d) "the real bar".  The reference itself
+cannot be imported (diffusers is absent), so this is the closest stand-in for "stock
+PyTorch on the same GPU".  Usage: python tests/eager_oracle_bench.py [steps]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "src")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+
+def main():
+    import bench
+    from oracle import ctsd as octsd
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+    cfg = bench.load_config()
+    B, T, V, C, H, W = cfg["latent_shape"]
+    steps = cfg["inference_steps"]
+    spi = steps // T
+    dev = torch.device("cuda", 0)
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        oracle = octsd.DiTCrossviewTemporalConditionModel(**cfg["model"])
+    torch.set_default_dtype(torch.float32)
+    bench.init_weights_(oracle)
+    oracle.eval()
+    cond = bench.synthetic_conditions(cfg, 2 * B, T, V, dev, torch.bfloat16)
+    lat = torch.randn(B, T, V, C, H, W, generator=torch.Generator().manual_seed(0)).to(dev)
+    sched = octsd.FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(steps)
+    sched.timesteps = sched.timesteps.to(dev)
+    sched.sigmas = sched.sigmas.to(dev)
+
+    def step(i, x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return octsd.df_denoise_step(oracle, sched, x, cond, i=i, steps_per_inference=spi,
+                                         guidance_scale=cfg["guidance_scale"],
+                                         model_dtype=torch.bfloat16)[0].float()
+
+    x = step(steps - 3, lat)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n):
+        x = step(steps - 3 + k % 3, x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    res = {"impl": "oracle restatement, eager PyTorch bf16 autocast + SDPA on the B200",
+           "ms_per_step": ms, "steps_per_s": 1000.0 / ms, "steps": n,
+           "executed_tflop_per_step": 447.4, "algorithmic_tflop_per_step": bench.F_STEP_TFLOP,
+           "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+    print(json.dumps(res))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "eager_oracle_bench.json"), "w") as f:
+        json.dump(res, f)
+
+
+if __name__ == "__main__":
+    main()
