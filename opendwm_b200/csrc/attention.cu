@@ -20,6 +20,7 @@
 #include "../../include/dwm_b200.h"
 
 namespace dwm {
+extern int g_attn_tc;   // -1: from env DWM_ATTN_LEGACY, 0: mma.sync kernel only, 1: tcgen05 kernel when eligible (gemm.cu)
 
 constexpr int HD = 64;
 
@@ -356,8 +357,8 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
   if (a->mask) DWM_REQUIRE(a->mask_div > 0 && a->n_outer > 0, "dwm_b200_attention: mask needs mask_div, n_outer");
   {
     // contiguous, unmasked sequences (joint / dual attention) run on tcgen05 + TMEM
-    static const bool legacy = getenv("DWM_ATTN_LEGACY") != nullptr;
-    if (!legacy && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
+    if (g_attn_tc < 0) g_attn_tc = getenv("DWM_ATTN_LEGACY") != nullptr ? 0 : 1;
+    if (g_attn_tc == 1 && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
   }
   const long long groups = static_cast<long long>(a->group_dims[0]) * a->group_dims[1] * a->group_dims[2];
   if (a->kv)

@@ -708,19 +708,26 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         if self.enable_temporal and self.shard is not None and \
                 self.shard.t_ways > 1:
             tp_sharded = self._temporal_qkv_attend_sharded(B, T, V, Hp, Wp, ws)
+        trace = getattr(self, "_trace", None)     # parity diagnostics only
         for i, b in enumerate(pk["blocks"]):
             res = residuals.pop(0) if residuals else None
             self._joint_block(b, ws, N, S, L, res)
+            if trace is not None:
+                trace(("joint", i), ws["x"])
             if self.enable_temporal and i in self.temporal_block_layers:
                 k = self.temporal_block_layers.index(i)
                 self.temporal_transformer_blocks[k].run(
                     pk["tp"][k], ws["x"], cd["temb_tab"][k], S, ws, tp_attend,
                     cd["t_alpha"][k], T * V * S, qkv_attend=tp_sharded)
+                if trace is not None:
+                    trace(("temporal", i), ws["x"])
             if self.enable_crossview and i in self.crossview_block_layers:
                 k = self.crossview_block_layers.index(i)
                 self.crossview_transformer_blocks[k].run(
                     pk["cv"][k], ws["x"], cd["vemb_tab"][k], S, ws, cv_attend,
                     cd["v_alpha"][k], T * V * S)
+                if trace is not None:
+                    trace(("crossview", i), ws["x"])
 
         # K8: AdaLayerNormContinuous (scale, shift) + proj_out
         fo, _ = pk["final_mod"]

@@ -27,7 +27,7 @@ def main():
         oracle = octsd.DiTCrossviewTemporalConditionModel(**cfg["model"])
     torch.set_default_dtype(torch.float32)
     bench.init_weights_(oracle)
-    oracle.eval()
+    oracle.to(dev).eval()
     cond = bench.synthetic_conditions(cfg, 2 * B, T, V, dev, torch.bfloat16)
     lat = torch.randn(B, T, V, C, H, W, generator=torch.Generator().manual_seed(0)).to(dev)
     sched = octsd.FlowMatchEulerDiscreteScheduler(shift=3.0)
