@@ -309,6 +309,13 @@ int dwm_b200_lincomb2(const float* x, const float* y, const float* s0, const flo
  * crossview_temporal_unet.py:729-731, 759-761). */
 int dwm_b200_axpy(const float* x, float* y, int64_t n, float a, dwm_stream_t stream);
 
+/* out[r, :] = softmax(scale * x[r, :]) for fp32 scores -> 16-bit probabilities.  Replaces
+ * the softmax inside F.scaled_dot_product_attention of the single-head (head_dim 512)
+ * mid-block Attention of diffusers AutoencoderKL (called by the reference at
+ * src/dwm/pipelines/ctsd.py:1633-1640, 2095-2098); Q K^T and P V run through dwm_b200_linear. */
+int dwm_b200_softmax_rows(const float* x, int64_t rows, int64_t cols, int64_t ld, float scale,
+                          void* out, int64_t ldo, int dtype, dwm_stream_t stream);
+
 /* Fused CFG combine + DDIM update (eta = 0) with per-(b,t,v) INT32 timesteps
  * (reference src/dwm/schedulers/temporal_independent.py:67-170 + ctsd.py:1548-1575):
  *   pred     fp32 [cfg * n_items * inner] (uncond half first), latent layout

@@ -274,6 +274,38 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
   }
 }
 
+// Row softmax of fp32 scores: out[r, c] = softmax_c(scale * x[r, c]) in 16 bits.  One CTA per
+// row; the row (<= 64 KB of fp32) is re-read from L2.  Used by the single-head, head_dim 512
+// mid-block attention of the 2-D AutoencoderKL decoder, where S = Q K^T and P V run as GEMMs.
+template <typename T>
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, long long ld, int cols,
+                                                           float scale_log2e, T* __restrict__ out, long long ldo) {
+  __shared__ float red[8];
+  const float* row = x + static_cast<long long>(blockIdx.x) * ld;
+  T* orow = out + static_cast<long long>(blockIdx.x) * ldo;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -INFINITY;
+  for (int c = tid; c < cols; c += 256) m = fmaxf(m, row[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = tid; c < cols; c += 256) sum += exp2f((row[c] - m) * scale_log2e);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int c = tid; c < cols; c += 256) orow[c] = Cvt<T>::from_f(exp2f((row[c] - m) * scale_log2e) * inv);
+}
+
 // Fused CFG combine + DDIM update (eta = 0) with per-(b,t,v) timesteps:
 //   pred: fp32 [cfg*B, T, V, C, H, W] (uncond half first);  lat (in/out): fp32 [B, T, V, C, H, W]
 //   ts: int32 [B, T, V] current timesteps; prev = ts - step_ratio; alphas: fp32 [num_train]
@@ -339,6 +371,23 @@ extern "C" int dwm_b200_axpy(const float* x, float* y, int64_t n, float a, dwm_s
   DWM_REQUIRE(x && y && n > 0, "dwm_b200_axpy: bad arguments");
   const unsigned grid = static_cast<unsigned>((n / 4 + 1 + 255) / 256);
   axpy_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, n, a);
+  DWM_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int dwm_b200_softmax_rows(const float* x, int64_t rows, int64_t cols, int64_t ld, float scale, void* out,
+                                     int64_t ldo, int dtype, dwm_stream_t stream) {
+  DWM_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols && ldo >= cols && rows < (1ll << 31) &&
+                  cols < (1ll << 31),
+              "dwm_b200_softmax_rows: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const float sl = scale * 1.4426950408889634f;
+  const unsigned grid = static_cast<unsigned>(rows);
+  if (dtype == DWM_BF16)
+    softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(x, ld, (int)cols, sl, static_cast<__nv_bfloat16*>(out), ldo);
+  else if (dtype == DWM_F16)
+    softmax_rows_kernel<__half><<<grid, 256, 0, s>>>(x, ld, (int)cols, sl, static_cast<__half*>(out), ldo);
+  else { set_last_error("dwm_b200_softmax_rows: bad dtype %d", dtype); return -1; }
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

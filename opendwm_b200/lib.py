@@ -111,6 +111,8 @@ SYMBOLS = {
         _p, ctypes.c_int, _p]),
     "dwm_b200_conv": (ctypes.c_int, [ctypes.POINTER(ConvArgs), _p]),
     "dwm_b200_axpy": (ctypes.c_int, [_p, _p, _i64, ctypes.c_float, _p]),
+    "dwm_b200_softmax_rows": (ctypes.c_int, [_p, _i64, _i64, _i64, ctypes.c_float, _p, _i64,
+                                            ctypes.c_int, _p]),
     "dwm_b200_lincomb2": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p]),
     "dwm_b200_cfg_ddim_step": (ctypes.c_int, [
         _p, ctypes.c_int, ctypes.c_float, _i64, _i64, _p, ctypes.c_int, _p,

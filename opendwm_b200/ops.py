@@ -443,6 +443,18 @@ def axpy(x, y, a=1.0):
     return y
 
 
+def softmax_rows(x, scale, out):
+    """out[r] = softmax(scale * x[r]) — fp32 [rows, cols] (row stride allowed) -> 16-bit."""
+    _f32(x, "x")
+    if x.dim() != 2 or out.dim() != 2 or x.shape != out.shape or x.stride(1) != 1 or \
+            out.stride(1) != 1:
+        raise ValueError("softmax_rows needs 2-D row-major tensors of equal shape")
+    _l.check(_l.load().dwm_b200_softmax_rows(
+        x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), float(scale), out.data_ptr(),
+        out.stride(0), _dt(out), _stream()), "dwm_b200_softmax_rows")
+    return out
+
+
 def cfg_ddim_step(pred, latents, timesteps, alphas_cumprod, *, cfg, guidance_scale,
                   step_ratio, final_alpha_cumprod, prediction_type,
                   round_dtype=torch.float32):

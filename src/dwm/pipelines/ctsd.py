@@ -237,14 +237,20 @@ class CrossviewTemporalSD:
         self.text_encoders = self.tokenizers = "pre-encoded"
         self.vae = common_config.get("vae_instance")
         self.is_temporal_vae = bool(common_config.get("vae_is_temporal", False))
-        vae_name = common_config.get("vae")
+        # reference :953-958: class named by common_config["vae"] (default
+        # "diffusers.AutoencoderKL"), loaded from <path>/vae; both map to the mirrors here
+        vae_name = common_config.get("vae", "diffusers.AutoencoderKL")
         vae_path = common_config.get(
             "vae_pretrained_model_name_or_path", pretrained_model_name_or_path)
-        if self.vae is None and vae_name is not None and vae_path is not None and \
-                vae_name.endswith("AutoencoderKLCogVideoX"):
-            from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
-            self.vae = AutoencoderKLCogVideoX.from_pretrained(
-                vae_path, subfolder="vae").to(self.device)
+        if self.vae is None and vae_path is not None and \
+                os.path.exists(os.path.join(vae_path, "vae", "config.json")):
+            if vae_name.endswith("AutoencoderKLCogVideoX"):
+                from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX as vae_type
+            elif vae_name.endswith("AutoencoderKL"):
+                from dwm.models.autoencoder_kl import AutoencoderKL as vae_type
+            else:
+                raise Exception("Unsupported VAE type {}.".format(vae_name))
+            self.vae = vae_type.from_pretrained(vae_path, subfolder="vae").to(self.device)
         if self.vae is not None and \
                 type(self.vae).__name__ == "AutoencoderKLCogVideoX":
             self.is_temporal_vae = True
