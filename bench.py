@@ -55,8 +55,12 @@ def peaks():
     if os.path.exists(path):
         with open(path) as f:
             d = json.load(f)
+        _PEAKS.update(d)
         return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs"), "measured"
     return 1400.0, 6650.0, "fallback"
+
+
+_PEAKS = {}
 
 
 class ClockSampler:
@@ -332,7 +336,10 @@ def run_native(args):
             "kernel_share_of_step": dom[1] / (ms * args.steps),
             "all_gemm_achieved": all_gemm, "all_gemm_launches": n_gemm,
             "gemm_share_of_step": gemm_ms / (ms * args.steps),
-            "peak_source": peak_src + " bf16_tflops_sustained",
+            "peak_source": peak_src + " bf16_tflops_sustained (cuBLAS inside a long step; "
+                           "the kernel may exceed it, see frac_of_burst_peak)",
+            "frac_of_burst_peak": (achieved / _PEAKS["bf16_tflops_burst"])
+            if achieved and _PEAKS.get("bf16_tflops_burst") else None,
             "step_frac_of_peak": (F_STEP_TFLOP / world / (ms * 1e-3) / peak_tf)
             if scale else None},
         "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s",
@@ -369,29 +376,41 @@ def run_native(args):
 
 def decode_latency(dev, dtype, V, C, H, W, ms_step):
     """Per-emitted-frame latency of the streaming loop: 3 denoise steps
-    + the 6-view temporal-VAE decode of the exiting frame exactly as
-    StreamingCrossviewTemporalSD.receive_frame issues it (frame + zero frame, reference
-    ctsd.py:1609-1621).  Untimed by the headline; reported beside it."""
+    + the 6-view decode of the exiting frame as StreamingCrossviewTemporalSD.receive_frame
+    issues it — with the SD-3.5 2-D AutoencoderKL the north-star config uses (reference
+    ctsd.py:2095-2098), and for comparison with the CogVideoX temporal VAE (frame + zero
+    frame, :1609-1621).  Untimed by the headline; reported beside it."""
+    from dwm.models.autoencoder_kl import AutoencoderKL
     from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
-    try:
-        torch.manual_seed(0)
-        with torch.device(dev):
-            vae = AutoencoderKLCogVideoX(compute_dtype=dtype)
-        cur = torch.randn(V, C, 1, H, W, device=dev)
-        z = torch.cat([cur, cur * 0], dim=2)
-        vae.decode(z, return_dict=False)                 # warm-up: packs weights
+
+    def timed(fn, n=3):
+        fn()                                             # warm-up: packs weights
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(3):
-            y = vae.decode(z, return_dict=False)[0]
+        for _ in range(n):
+            y = fn()
         e1.record()
         torch.cuda.synchronize()
-        dec = e0.elapsed_time(e1) / 3
-        return {"ms": 3 * ms_step + dec, "decode_ms": dec, "denoise_ms": 3 * ms_step,
-                "decode_out_shape": list(y.shape),
-                "definition": "3 denoise steps (spi) + CogVideoX decode of 6 views x "
-                              "(frame, zero frame) at 256x448"}
+        return e0.elapsed_time(e1) / n, list(y.shape)
+    try:
+        torch.manual_seed(0)
+        with torch.device(dev):
+            vae2d = AutoencoderKL(
+                block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                latent_channels=C, norm_num_groups=32, scaling_factor=1.5305,
+                shift_factor=0.0609, use_quant_conv=False, use_post_quant_conv=False,
+                compute_dtype=dtype)
+            vae3d = AutoencoderKLCogVideoX(compute_dtype=dtype)
+        cur = torch.randn(V, C, H, W, device=dev).to(dtype)
+        dec2, shp2 = timed(lambda: vae2d.decode(cur, return_dict=False)[0])
+        z = torch.cat([cur[:, :, None], cur[:, :, None] * 0], dim=2).float()
+        dec3, shp3 = timed(lambda: vae3d.decode(z, return_dict=False)[0])
+        return {"ms": 3 * ms_step + dec2, "decode_ms": dec2, "denoise_ms": 3 * ms_step,
+                "decode_out_shape": shp2,
+                "definition": "3 denoise steps (spi) + SD-3.5 AutoencoderKL decode of the "
+                              "6 views of the exiting frame at 256x448",
+                "cogvideox_decode_ms": dec3, "cogvideox_decode_out_shape": shp3}
     except Exception as e:                               # never lose the headline line
         return {"error": repr(e)[:200]}
 

@@ -191,13 +191,17 @@ class AutoencoderKL(torch.nn.Module):
             return p
 
         lc = self.config.latent_channels
-        pk = dict(conv_in=conv3(d.conv_in, pad_in=pad8(lc)))
         if hasattr(self, "post_quant_conv"):
-            w = torch.zeros(pad8(lc), pad8(lc), device=dev, dtype=dt)
+            # 1x1 conv as a GEMM whose N is padded to the 32-column tile granule; conv_in
+            # then reads those 32 (zero-extended) channels
+            cq = (lc + 31) // 32 * 32
+            w = torch.zeros(cq, pad8(lc), device=dev, dtype=dt)
             w[:lc, :lc] = self.post_quant_conv.weight.detach().reshape(lc, lc).to(dev, dt)
-            b = torch.zeros(pad8(lc), device=dev)
+            b = torch.zeros(cq, device=dev)
             b[:lc] = self.post_quant_conv.bias.detach().float()
-            pk["pq"] = (w, b)
+            pk = dict(pq=(w, b), conv_in=conv3(d.conv_in, pad_in=cq))
+        else:
+            pk = dict(conv_in=conv3(d.conv_in, pad_in=pad8(lc)))
         pk["mid"] = [res(r) for r in d.mid_block.resnets]
         pk["attn"] = None
         if len(d.mid_block.attentions):
@@ -279,11 +283,11 @@ class AutoencoderKL(torch.nn.Module):
             self._pack()
         pk, dt = self._pk, self.compute_dtype
         nb, lc, H, W = z.shape
-        cp = pk["conv_in"][0].shape[2]
+        cp = pk["pq"][0].shape[1] if "pq" in pk else pk["conv_in"][0].shape[2]
         x16 = torch.zeros(nb, 1, H, W, cp, device=z.device, dtype=dt)
         x16[..., :lc] = z.permute(0, 2, 3, 1).unsqueeze(1)
         if "pq" in pk:
-            x16 = _ops.linear(x16.view(-1, cp), *pk["pq"]).view(nb, 1, H, W, cp)
+            x16 = _ops.linear(x16.view(-1, cp), *pk["pq"]).view(nb, 1, H, W, -1)
         h = _ops.conv(x16, *pk["conv_in"], kernel=(1, 3, 3), epilogue=_lib.EPI_F32)
         shape = (nb, H, W)
         h = self._resnet(h, shape, pk["mid"][0])

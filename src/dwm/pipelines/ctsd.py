@@ -370,6 +370,43 @@ class CrossviewTemporalSD:
             round_dtype=self.model_dtype)
         return latents
 
+    def denoise_step_graphed(self, latents, conditions, idx, timesteps, in_range=None):
+        """`denoise_step` replayed from a CUDA graph (single GPU, fixed shapes and a fixed
+        condition set): the small per-step tensors are copied into static buffers, the
+        ~600 (UNet) / ~540 (DiT) launches of the step are submitted with one
+        cudaGraphLaunch.  The first call per (latents, conditions) pair runs one eager
+        warm-up step on a scratch copy (lazy weight packing, condition caches, workspace)
+        and captures."""
+        if self.sharding is not None:
+            return self.denoise_step(latents, conditions, idx, timesteps, in_range)
+        key = (latents.data_ptr(), tuple(latents.shape), idx is None, in_range is None,
+               tuple(sorted((k, v.data_ptr()) for k, v in conditions.items()
+                            if torch.is_tensor(v))))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            st = dict(idx=None if idx is None else idx.clone(), ts=timesteps.clone(),
+                      rng=None if in_range is None else in_range.clone())
+            backup = latents.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.denoise_step(latents, conditions, st["idx"], st["ts"], st["rng"])
+            torch.cuda.current_stream().wait_stream(side)
+            latents.copy_(backup)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.denoise_step(latents, conditions, st["idx"], st["ts"], st["rng"])
+            g = graphs[key] = (graph, st)
+        graph, st = g
+        if idx is not None:
+            st["idx"].copy_(idx)
+        st["ts"].copy_(timesteps)
+        if in_range is not None:
+            st["rng"].copy_(in_range)
+        graph.replay()
+        return latents
+
     def _denoise_step_unet(self, latents, conditions, timesteps, do_cfg):
         """CTSD-2.1 step: CFG batching, UNet forward, fused CFG + DDIM (eta 0) update
         (reference ctsd.py:1536-1575 with the in-repo DDIMScheduler.step)."""
@@ -451,6 +488,11 @@ class CrossviewTemporalSD:
         ts_table = self.test_scheduler.timesteps.to(self.device).float()
         inject = (not df_mode) and image_latents is not None and \
             reference_frame_count > 0
+        # opt-in CUDA-graph replay of the step (inference_config["cuda_graph"] or env
+        # DWM_CUDA_GRAPH=1): conditions are fixed for the whole window here
+        use_graph = self.inference_config.get(
+            "cuda_graph", os.environ.get("DWM_CUDA_GRAPH", "0") == "1")
+        step = self.denoise_step_graphed if use_graph else self.denoise_step
         for i in range(start_timestep, stop_timestep):
             if df_mode:
                 idx, timesteps, in_range = self._df_step_tensors(
@@ -468,7 +510,7 @@ class CrossviewTemporalSD:
                 latents[:, :reference_frame_count] = ref
                 timesteps = timesteps.clone()
                 timesteps[:, :reference_frame_count] = 0
-            self.denoise_step(latents, conditions, idx, timesteps, in_range)
+            step(latents, conditions, idx, timesteps, in_range)
         if df_mode:
             cur = latents[:, take_time].flatten(0, 1)
             if self.is_temporal_vae and self.vae is not None:

@@ -13,7 +13,63 @@ for p in (ROOT, os.path.join(ROOT, "src")):
 import torch  # noqa: E402
 
 
+def unet_main(n):
+    """Config 2: the oracle UNet restatement, eager bf16 autocast, one CFG step."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from unet_bench import MODEL
+    from oracle import unet as ounet
+    from oracle.ctsd import DDIMSchedulerOracle
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    with torch.device(dev):
+        o = ounet.UNetCrossviewTemporalConditionModel(**MODEL)
+    o.to(dev).eval()
+    B, T, V = 1, 1, 6
+    g = torch.Generator().manual_seed(0)
+    ring = torch.zeros(V, V, dtype=torch.bool)
+    for i in range(V):
+        for d in (-1, 0, 1):
+            ring[i, (i + d) % V] = True
+    cond = dict(
+        encoder_hidden_states=(torch.randn(2 * B, T, V, 77, 1024, generator=g) * 0.1).to(dev),
+        condition_image_tensor=None,
+        disable_crossview=torch.zeros(2 * B, dtype=torch.bool, device=dev),
+        disable_temporal=torch.ones(2 * B, dtype=torch.bool, device=dev),
+        crossview_attention_mask=ring.unsqueeze(0).repeat(2 * B, 1, 1).to(dev),
+        added_time_ids=torch.randn(2 * B, T, V, 11, generator=g).to(dev))
+    lat = torch.randn(B, T, V, 4, 32, 56, generator=g).to(dev)
+    sch = DDIMSchedulerOracle(beta_start=0.00085, beta_end=0.012)
+    sch.set_timesteps(50)
+
+    def step(x, t):
+        tt = torch.full((2 * B, T, V), t, device=dev)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = o(torch.cat([x, x]), tt.float(), **cond)[0].float()
+        u, c = out.chunk(2)
+        return sch.step(u + 3.0 * (c - u), tt[:B], x)
+
+    ts = sch.timesteps.tolist()
+    x = step(lat, ts[0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n):
+        x = step(x, ts[1 + k])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    res = {"impl": "oracle UNet restatement, eager PyTorch bf16 autocast + SDPA on the B200",
+           "workload": "ctsd_21 6-view image step [2,1,6,4,32,56]", "ms_per_step": ms,
+           "steps_per_s": 1000.0 / ms, "steps": n}
+    print(json.dumps(res))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "eager_oracle_unet_bench.json"), "w") as f:
+        json.dump(res, f)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "unet":
+        return unet_main(int(sys.argv[2]) if len(sys.argv) > 2 else 10)
     import bench
     from oracle import ctsd as octsd
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 3

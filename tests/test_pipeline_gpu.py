@@ -146,3 +146,40 @@ def test_unet_ddim_pipeline_matches_oracle_loop():
             lat = sch.step(u + 3.0 * (c - u), tt[:B], lat)
     err = ((r["latents"] - lat).abs().max() / lat.abs().max()).item()
     assert err < 8e-3, err
+
+
+def test_cuda_graph_step_is_bit_identical():
+    """denoise_step_graphed (one cudaGraphLaunch per step) == denoise_step, DiT and UNet."""
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    from test_unet import UCFG, _oracle, _inputs
+    # DiT, diffusion forcing
+    pipe, _ = _pipe(TINY, {"guidance_scale": 2.0, "inference_steps": 12,
+                           "sequence_length_per_iteration": 4},
+                    {"frame_prediction_style": "diffusion_forcing"})
+    sample, _, cond = synthetic_inputs(TINY, device="cuda")
+    pipe.reset_streaming((1, 4, 3, 16, 8, 12), "pt")
+    a, b = sample[:1].clone().float(), sample[:1].clone().float()
+    for i in (9, 10, 11):
+        idx, ts, rng = pipe._df_step_tensors(i, 4, 3, 0, 1, 3)
+        pipe.denoise_step(a, cond, idx, ts, rng)
+        pipe.denoise_step_graphed(b, cond, idx, ts, rng)
+    assert len(pipe._graphs) == 1
+    assert torch.equal(a, b) and not torch.equal(a, sample[:1])
+    # UNet, DDIM
+    o = _oracle(UCFG)
+    m = U(**UCFG, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    pipe = CrossviewTemporalSD(None, {"generator_seed": 0}, "cuda",
+                               {"frame_prediction_style": "ctsd"}, {},
+                               {"guidance_scale": 3.0, "inference_steps": 4}, None, m,
+                               model_dtype=torch.float32)
+    pipe.test_scheduler.set_timesteps(4, "cuda")
+    x, _, c = _inputs(2, 2, 2)
+    c = {k: (v.cuda() if v is not None else None) for k, v in c.items()}
+    a, b = x[:1].clone().cuda(), x[:1].clone().cuda()
+    for t in pipe.test_scheduler.timesteps.tolist():
+        ts = torch.full((1, 2, 2), t, dtype=torch.int32, device="cuda")
+        pipe.denoise_step(a, c, None, ts, None)
+        pipe.denoise_step_graphed(b, c, None, ts, None)
+    assert torch.equal(a, b) and torch.isfinite(a).all()

@@ -63,25 +63,31 @@ def main():
     lat = torch.randn(B, T, V, 4, 32, 56, generator=gen).to(dev)
     tsched = pipe.test_scheduler.timesteps
 
-    def step(k):
-        ts = tsched[k % 50].to(torch.int32).expand(B, T, V).contiguous()
-        pipe.denoise_step(lat, cond, None, ts, None)
+    ts_list = [tsched[k].to(torch.int32).expand(B, T, V).contiguous() for k in range(50)]
 
-    for k in range(3):
-        step(k)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ops.profile_begin()
-    e0.record()
-    for k in range(steps):
-        step(3 + k)
-    e1.record()
-    torch.cuda.synchronize()
-    prof = ops.profile_end()
-    ms = e0.elapsed_time(e1) / steps
+    def run(fn, count_launches):
+        for k in range(3):
+            fn(lat, cond, None, ts_list[k % 50], None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if count_launches:
+            ops.profile_begin()
+        e0.record()
+        for k in range(steps):
+            fn(lat, cond, None, ts_list[(3 + k) % 50], None)
+        e1.record()
+        torch.cuda.synchronize()
+        n = ops.profile_end()["launches"] / steps if count_launches else None
+        return e0.elapsed_time(e1) / steps, n
+
+    ms_eager, launches = run(pipe.denoise_step, True)
+    lat.normal_(generator=None)
+    ms, _ = run(pipe.denoise_step_graphed, False)
     res = dict(workload="ctsd_21 6-view image step [2,1,6,4,32,56], CFG 3, DDIM", ms_per_step=ms,
                steps_per_s=1000.0 / ms, tflop_per_step=F_STEP_TFLOP,
-               tflops=F_STEP_TFLOP / ms * 1e3, launches_per_step=prof["launches"] / steps,
+               tflops=F_STEP_TFLOP / ms * 1e3, launches_per_step=launches,
+               ms_per_step_without_cuda_graph=ms_eager,
+               mode="CUDA-graph replay of the step (denoise_step_graphed)",
                finite=bool(torch.isfinite(lat).all()))
     print(json.dumps(res))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
