@@ -338,8 +338,8 @@ def run_native(args):
             "gemm_share_of_step": gemm_ms / (ms * args.steps),
             "peak_source": peak_src + " bf16_tflops_sustained (cuBLAS inside a long step; "
                            "the kernel may exceed it, see frac_of_burst_peak)",
-            "frac_of_burst_peak": (achieved / _PEAKS["bf16_tflops_burst"])
-            if achieved and _PEAKS.get("bf16_tflops_burst") else None,
+            "frac_of_burst_peak": (achieved / _PEAKS["bf16_tflops"])
+            if achieved and _PEAKS.get("bf16_tflops") else None,
             "step_frac_of_peak": (F_STEP_TFLOP / world / (ms * 1e-3) / peak_tf)
             if scale else None},
         "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s",

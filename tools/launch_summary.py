@@ -1,24 +1,28 @@
 """Summarises an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel
-totals of ONE denoise step (delimited by the patchify kernel that starts each step)."""
+totals of ONE denoise step (delimited by the patchify kernel that starts each DiT step, or
+e.g. "end:cfg_ddim" for the UNet step).  usage: launch_summary.py csv [out] [delim] [detail]"""
 import collections
 import csv
 import re
 import sys
 
 
-def main(path, out=None):
+def main(path, out=None, delim="patchify", detail=False):
     rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
     names = [(r[ki], float(r[vi].replace(",", "")) / 1e6, r[gi]) for r in data if len(r) > vi]
-    starts = [i for i, (n, _, _) in enumerate(names) if "patchify" in n]
+    # delim "x": a step starts at each kernel whose name contains x; "end:x": ends at it
+    end = delim.startswith("end:")
+    key = delim[4:] if end else delim
+    starts = [i + (1 if end else 0) for i, (n, _, _) in enumerate(names) if key in n]
     a, b = starts[-2], starts[-1]
     step = names[a:b]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, ms, grid in step:
         k = re.sub(r"^void ", "", n.split("(")[0]).replace("dwm::", "")
-        if "attn_kernel" in k:
+        if detail or "attn_kernel" in k:
             k += " grid=" + grid.replace(" ", "")
         agg[k][0] += 1
         agg[k][1] += ms
@@ -34,4 +38,5 @@ def main(path, out=None):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None,
+         sys.argv[3] if len(sys.argv) > 3 else "patchify", len(sys.argv) > 4)
