@@ -2,6 +2,8 @@
 // GroupNorm statistics, the fused SpatialNorm3D (GroupNorm * conv_y(zq) + conv_b(zq)) +
 // SiLU that writes the 16-bit, causally time-padded input of the next convolution, and
 // the nearest-neighbour (space / space-time) upsampler.
+#include <algorithm>
+
 #include "common.cuh"
 #include "../../include/dwm_b200.h"
 
@@ -44,7 +46,52 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   }
 }
 
-// generic variant: any C, any group size (scalar loads; UNet widths 320 / 960 / 1920 ...)
+// wide variant: any C % 4 == 0 with C / 4 <= 1024 and any group size (UNet widths 320 ... 2560,
+// 10 / 20 / 40 ... channels per group).  blockDim = (C/4) * k so that every thread keeps ONE
+// channel quad for all its pixels: per-element register sums, then at most 4 shared atomics
+// per thread and one double atomic per (block, group).
+__global__ void __launch_bounds__(1024) gn_stats_wide_kernel(const float* __restrict__ x, long long pixels, int C, int G,
+                                                             long long pixels_per_block, double* __restrict__ sums) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int vec = C >> 2;
+  if (tid < 64) { s_sum[tid] = 0.f; s_sq[tid] = 0.f; }
+  __syncthreads();
+  const int c4 = tid % vec, prow = tid / vec, k = blockDim.x / vec;
+  const long long p0 = static_cast<long long>(blockIdx.x) * pixels_per_block;
+  long long p1 = p0 + pixels_per_block;
+  if (p1 > pixels) p1 = pixels;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  const float4* base = reinterpret_cast<const float4*>(x + static_cast<long long>(n) * pixels * C);
+  for (long long p = p0 + prow; p < p1; p += k) {
+    const float4 v = base[p * vec + c4];
+    s0 += v.x; q0 += v.x * v.x;
+    s1 += v.y; q1 += v.y * v.y;
+    s2 += v.z; q2 += v.z * v.z;
+    s3 += v.w; q3 += v.w * v.w;
+  }
+  const int cg = C / G;
+  const float ss[4] = {s0, s1, s2, s3}, qq[4] = {q0, q1, q2, q3};
+  int cur = (c4 * 4) / cg;
+  float a = 0.f, b = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int g = (c4 * 4 + e) / cg;
+    if (g != cur) {
+      atomicAdd(&s_sum[cur], a); atomicAdd(&s_sq[cur], b);
+      cur = g; a = 0.f; b = 0.f;
+    }
+    a += ss[e]; b += qq[e];
+  }
+  atomicAdd(&s_sum[cur], a); atomicAdd(&s_sq[cur], b);
+  __syncthreads();
+  if (tid < G) {
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2], static_cast<double>(s_sum[tid]));
+    atomicAdd(&sums[(static_cast<long long>(n) * G + tid) * 2 + 1], static_cast<double>(s_sq[tid]));
+  }
+}
+
+// last-resort variant (C / 4 > 1024): any C, any group size (scalar loads; UNet widths 320 / 960 / 1920 ...)
 __global__ void __launch_bounds__(256) gn_stats_generic_kernel(const float* __restrict__ x, long long pixels, int C,
                                                                int G, long long pixels_per_block,
                                                                double* __restrict__ sums) {
@@ -183,11 +230,29 @@ extern "C" int dwm_b200_groupnorm_stats(const float* x, int64_t nb, int64_t pixe
               "dwm_b200_groupnorm_stats: need C %% 4 == 0, C %% groups == 0, groups <= 64 (got C=%d, groups=%d)", C, groups);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   DWM_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * nb * groups, s));
-  const bool fast = (C / groups) % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0;
-  const long long ppb = fast ? 1024 : 64;
-  dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
-  if (fast) gn_stats_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
-  else gn_stats_generic_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  const int vec = C / 4;
+  const bool fast = (C / groups) % 4 == 0 && vec <= 256 && 256 % vec == 0;
+  // pixels per block: about 4 blocks per SM over the whole launch, whole thread-rows per block
+  auto pick = [&](long long rows_per_iter) {
+    const long long target = std::max<long long>(1, 592 / nb);
+    const long long chunks = std::min((pixels + rows_per_iter - 1) / rows_per_iter, target);
+    const long long ppb = (pixels + chunks - 1) / chunks;
+    return (ppb + rows_per_iter - 1) / rows_per_iter * rows_per_iter;
+  };
+  if (fast) {
+    const long long ppb = pick(256 / vec);
+    dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
+    gn_stats_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  } else if (vec <= 1024) {
+    const int k = std::max(1, 256 / vec);
+    const long long ppb = pick(k);
+    dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
+    gn_stats_wide_kernel<<<grid, vec * k, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  } else {
+    const long long ppb = 64;
+    dim3 grid(static_cast<unsigned>((pixels + ppb - 1) / ppb), static_cast<unsigned>(nb));
+    gn_stats_generic_kernel<<<grid, 256, 0, s>>>(x, pixels, C, groups, ppb, sums);
+  }
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
