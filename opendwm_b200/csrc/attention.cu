@@ -337,6 +337,8 @@ static int launch_attn(const AttnParams& p, cudaStream_t s) {
 // attention_tc.cu
 bool attn_tc_eligible(const dwm_attention_args* a);
 int attn_tc_launch(const dwm_attention_args* a, cudaStream_t s);
+// attention_tc2.cu (two co-resident CTAs per SM, O in TMEM)
+int attn_tc2_launch(const dwm_attention_args* a, cudaStream_t s);
 
 }  // namespace dwm
 
@@ -358,6 +360,7 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
   {
     // contiguous, unmasked sequences (joint / dual attention) run on tcgen05 + TMEM
     if (g_attn_tc < 0) g_attn_tc = getenv("DWM_ATTN_LEGACY") != nullptr ? 0 : 1;
+    if (g_attn_tc == 2 && attn_tc_eligible(a)) return attn_tc2_launch(a, reinterpret_cast<cudaStream_t>(stream));
     if (g_attn_tc == 1 && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
   }
   const long long groups = static_cast<long long>(a->group_dims[0]) * a->group_dims[1] * a->group_dims[2];

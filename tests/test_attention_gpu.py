@@ -28,8 +28,18 @@ def _tol(dtype):
     return 1.2e-2 if dtype == torch.bfloat16 else 2e-3
 
 
+@pytest.fixture(params=[1, 2], ids=["tc1", "tc2"])
+def tc_variant(request):
+    """Both tcgen05 attention kernels: 1 = attention_tc.cu (one CTA per SM, O in registers),
+    2 = attention_tc2.cu (two CTAs per SM, O in TMEM with lazy rescale)."""
+    from opendwm_b200 import lib
+    lib.set_option("attn_tc", request.param)
+    yield request.param
+    lib.set_option("attn_tc", -1)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-def test_joint_split(dtype):
+def test_joint_split(dtype, tc_variant):
     from opendwm_b200 import ops
     N, S, L, heads = 3, 448, 154, 3
     D = heads * 64
@@ -109,11 +119,33 @@ def test_temporal(T, kind):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("seq,N,heads", [(448, 5, 4), (129, 3, 2), (200, 7, 1), (640, 2, 3),
                                          (65, 4, 2), (602, 40, 24)])
-def test_contiguous_sequences_tcgen05(seq, N, heads, dtype):
+def test_contiguous_sequences_tcgen05(seq, N, heads, dtype, tc_variant):
     """Contiguous unmasked groups take the tcgen05/TMEM kernel (attention_tc.cu)."""
     from opendwm_b200 import ops
     D = heads * 64
     qkv = _qkv(N * seq, D, dtype, seed=seq)
+    out = torch.zeros(N * seq, D, dtype=dtype, device="cuda")
+    ops.attention(qkv, out, D=D, heads=heads, group_dims=[N], group_strides=[seq], seq=seq)
+    idx = torch.arange(N * seq, device="cuda").view(N, seq)
+    ref = _ref(qkv, idx, D, heads)
+    err = ((out.view(N, seq, D).float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < _tol(dtype), err
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_growing_logits_exercise_rescale(dtype, tc_variant):
+    """Keys of later blocks carry much larger logits, so the running max grows by far more
+    than 2^8 between key blocks (the lazy-rescale branch of attention_tc2.cu) and also by
+    small steps (the no-rescale branch)."""
+    from opendwm_b200 import ops
+    N, seq, heads = 3, 602, 2
+    D = heads * 64
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(N * seq, 3 * D, generator=g)
+    ramp = torch.linspace(0.2, 6.0, seq).repeat(N).unsqueeze(1)     # |k| grows along the sequence
+    x[:, D:2 * D] *= ramp
+    x[:, :D] *= 2.0
+    qkv = x.to(dtype).cuda()
     out = torch.zeros(N * seq, D, dtype=dtype, device="cuda")
     ops.attention(qkv, out, D=D, heads=heads, group_dims=[N], group_strides=[seq], seq=seq)
     idx = torch.arange(N * seq, device="cuda").view(N, seq)

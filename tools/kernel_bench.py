@@ -31,13 +31,17 @@ def main():
     f = lambda: ops.attention(qkv, o, D=D, heads=heads, group_dims=[N], group_strides=[S + L],
                               seq=S + L, out_group_strides=[S], out_stride_outer=0,
                               out_stride_inner=1, split=S, out2=o2)
-    t = timeit(f)
+    from opendwm_b200 import lib
     fl = 4.0 * (S + L) ** 2 * D * N
-    res["joint_attention"] = dict(ms=t, tflops=fl / t / 1e9)
     qs = torch.randn(N * S, 3 * D, device="cuda").to(dt)
-    f = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[N], group_strides=[S], seq=S)
-    t = timeit(f)
-    res["dual_attention"] = dict(ms=t, tflops=4.0 * S * S * D * N / t / 1e9)
+    f2 = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[N], group_strides=[S], seq=S)
+    for variant, tag in ((1, ""), (2, "_tc2")):
+        lib.set_option("attn_tc", variant)
+        t = timeit(f)
+        res["joint_attention" + tag] = dict(ms=t, tflops=fl / t / 1e9)
+        t = timeit(f2)
+        res["dual_attention" + tag] = dict(ms=t, tflops=4.0 * S * S * D * N / t / 1e9)
+    lib.set_option("attn_tc", -1)
     # temporal pointwise (B'=2, T=16, V=6)
     B, T, V = 2, 16, 6
     f = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[B, V * S],
