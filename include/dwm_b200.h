@@ -104,8 +104,9 @@ const char* dwm_b200_version(void);
 const char* dwm_b200_last_error(void);
 /* Runtime switches: "gemm_2cta" = 1 routes dwm_b200_linear (M >= 512) to the 2-CTA
  * cta_group::2 kernel, 0 to the 1-CTA kernel (default: env DWM_GEMM_2CTA, else 1);
- * "attn_tc" = 1 routes eligible (contiguous, unmasked, head_dim 64) attention to the
- * tcgen05 kernel, 0 keeps the mma.sync kernel (default 1 unless env DWM_ATTN_LEGACY). */
+ * "attn_tc" routes eligible (contiguous, unmasked, head_dim 64) attention: 2 = tcgen05
+ * kernel with two co-resident CTAs per SM and O in TMEM (default), 1 = first-generation
+ * tcgen05 kernel, 0 = mma.sync kernel, -1 = re-read env DWM_ATTN_TC / DWM_ATTN_LEGACY. */
 int dwm_b200_set_option(const char* name, int value);
 
 /* y = epilogue(A @ W^T): replaces every torch.nn.Linear / 1x1 / patchify conv on the

@@ -20,7 +20,7 @@
 #include "../../include/dwm_b200.h"
 
 namespace dwm {
-extern int g_attn_tc;   // -1: from env DWM_ATTN_LEGACY, 0: mma.sync kernel only, 1: tcgen05 kernel when eligible (gemm.cu)
+extern int g_attn_tc;   // -1: from env, 0: mma.sync kernel only, 1 / 2: attention_tc.cu / attention_tc2.cu when eligible (gemm.cu)
 
 constexpr int HD = 64;
 
@@ -359,7 +359,10 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
   if (a->mask) DWM_REQUIRE(a->mask_div > 0 && a->n_outer > 0, "dwm_b200_attention: mask needs mask_div, n_outer");
   {
     // contiguous, unmasked sequences (joint / dual attention) run on tcgen05 + TMEM
-    if (g_attn_tc < 0) g_attn_tc = getenv("DWM_ATTN_LEGACY") != nullptr ? 0 : 1;
+    if (g_attn_tc < 0) {   // env DWM_ATTN_TC = 0 | 1 | 2 (DWM_ATTN_LEGACY: same as 0); default 2
+      const char* e = getenv("DWM_ATTN_TC");
+      g_attn_tc = getenv("DWM_ATTN_LEGACY") != nullptr ? 0 : (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    }
     if (g_attn_tc == 2 && attn_tc_eligible(a)) return attn_tc2_launch(a, reinterpret_cast<cudaStream_t>(stream));
     if (g_attn_tc == 1 && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
   }

@@ -122,7 +122,7 @@ def main():
         torch.cuda.synchronize()
         res[tag] = {"stages": out, "out": rel(y, ref)}
         for k in opts:
-            lib.set_option(k, 1)
+            lib.set_option(k, -1)
     run_native(model, cond, "native_bf16")
     run_native(model, cond, "native_bf16_legacy_kernels", gemm_2cta=0, attn_tc=0)
     del model
