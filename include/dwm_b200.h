@@ -106,7 +106,9 @@ const char* dwm_b200_last_error(void);
  * cta_group::2 kernel, 0 to the 1-CTA kernel (default: env DWM_GEMM_2CTA, else 1);
  * "attn_tc" routes eligible (contiguous, unmasked, head_dim 64) attention: 2 = tcgen05
  * kernel with two co-resident CTAs per SM and O in TMEM (default), 1 = first-generation
- * tcgen05 kernel, 0 = mma.sync kernel, -1 = re-read env DWM_ATTN_TC / DWM_ATTN_LEGACY. */
+ * tcgen05 kernel, 0 = mma.sync kernel, -1 = re-read env DWM_ATTN_TC / DWM_ATTN_LEGACY;
+ * "ln_staged" = 1 (default) runs large LayerNorms through the bulk-copy staged kernel, 0
+ * keeps the register-resident kernel. */
 int dwm_b200_set_option(const char* name, int value);
 
 /* y = epilogue(A @ W^T): replaces every torch.nn.Linear / 1x1 / patchify conv on the

@@ -109,7 +109,7 @@ __device__ __forceinline__ long long key_row(const AttnParams& p, long long base
 
 // NW warps per CTA, 16 query rows per warp, KVT keys per streamed tile.
 template <typename T, int NW, int KVT>
-__global__ void __launch_bounds__(NW * 32) attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(NW * 32, NW == 4 ? 4 : 1) attn_kernel(const AttnParams p) {
   constexpr int QROWS = NW * 16;
   constexpr int NT = NW * 32;
   __shared__ __align__(128) uint8_t sq[QROWS * 128];

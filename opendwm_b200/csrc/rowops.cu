@@ -22,24 +22,15 @@ struct LnParams {
 
 constexpr int LN_WARPS = 4;   // rows per block (one warp per row)
 
-template <typename T, int VPL, bool DUAL>
-__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_kernel(const LnParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m = blockIdx.x * LN_WARPS + warp;
-  if (m >= p.M) return;
-  const int nvec = p.D >> 2;
+// Everything after the x row sits in registers: optional adds, statistics, write-back of the
+// summed row, affine / AdaLN modulation (optionally two modulations), 16-bit stores.
+// EXACT: D / 4 == 32 * VPL, so the per-vector bounds checks fold away.
+template <typename T, int VPL, bool DUAL, bool EXACT>
+__device__ __forceinline__ void ln_finish(const LnParams& p, const int m, const int lane, float4 (&v)[VPL]) {
+  const int nvec = EXACT ? 32 * VPL : (p.D >> 2);
   const int item = p.rows_per_item > 0 ? m / p.rows_per_item : 0;
-  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(m) * p.ldx);
   const float4* ai = p.add_item ? reinterpret_cast<const float4*>(p.add_item + static_cast<long long>(item) * p.add_item_ld) : nullptr;
   const float4* af = p.add_full ? reinterpret_cast<const float4*>(p.add_full + static_cast<long long>(m) * p.add_full_ld) : nullptr;
-  float4 v[VPL];
-  // all loads of the row are issued back to back (no control flow in between) so that
-  // VPL 16-byte requests per lane are in flight; the optional adds follow.
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int idx = lane + 32 * i;
-    v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   if (ai) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -136,9 +127,115 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_kernel(const LnParams
   store_vec(v, o1);
 }
 
+template <typename T, int VPL, bool DUAL>
+__global__ void __launch_bounds__(LN_WARPS * 32) layernorm_kernel(const LnParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * LN_WARPS + warp;
+  if (m >= p.M) return;
+  const int nvec = p.D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<long long>(m) * p.ldx);
+  float4 v[VPL];
+  // all loads of the row are issued back to back (no control flow in between) so that
+  // VPL 16-byte requests per lane are in flight; the optional adds follow.
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int idx = lane + 32 * i;
+    v[i] = idx < nvec ? xr[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  ln_finish<T, VPL, DUAL, false>(p, m, lane, v);
+}
+
+// Staged variant: a producer thread streams groups of 8 rows into a 3-stage shared-memory ring
+// with 1-D bulk copies (cp.async.bulk + mbarrier transaction counts); 8 compute warps take
+// one row each.  Memory-level parallelism (72-144 KB in flight per SM) no longer depends on
+// occupancy — the register-resident kernel above stalls on long_scoreboard at 31 % occupancy.
+constexpr int LNS_ROWS = 8, LNS_STAGES = 3, LNS_THREADS = (LNS_ROWS + 1) * 32;
+
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename T, int VPL, bool DUAL, bool EXACT>
+__global__ void __launch_bounds__(LNS_THREADS, 1) layernorm_staged_kernel(const LnParams p, const int n_groups) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int row_bytes = p.D * 4;
+  float* stages = reinterpret_cast<float*>(ln_smem);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ln_smem + static_cast<size_t>(LNS_STAGES) * LNS_ROWS * row_bytes);
+  uint64_t* empty = full + LNS_STAGES;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < LNS_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], LNS_ROWS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int st = 0;
+  uint32_t ph = 0;
+  if (warp == LNS_ROWS) {
+    if (lane == 0) {
+      for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        mbar_wait(&empty[st], ph ^ 1);
+        const int m0 = g * LNS_ROWS;
+        const int rows = p.M - m0 < LNS_ROWS ? p.M - m0 : LNS_ROWS;
+        mbar_expect_tx(&full[st], static_cast<uint32_t>(rows) * row_bytes);
+        for (int r = 0; r < rows; ++r)
+          bulk_g2s(stages + static_cast<size_t>(st * LNS_ROWS + r) * p.D,
+                   p.x + static_cast<long long>(m0 + r) * p.ldx, row_bytes, &full[st]);
+        if (++st == LNS_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+    return;
+  }
+  const int nvec = EXACT ? 32 * VPL : (p.D >> 2);
+  for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    mbar_wait(&full[st], ph);
+    const int m = g * LNS_ROWS + warp;
+    float4 v[VPL];
+    if (m < p.M) {
+      const float4* row = reinterpret_cast<const float4*>(stages + static_cast<size_t>(st * LNS_ROWS + warp) * p.D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int idx = lane + 32 * i;
+        v[i] = (EXACT || idx < nvec) ? row[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);      // the row sits in registers: release the stage
+    if (m < p.M) ln_finish<T, VPL, DUAL, EXACT>(p, m, lane, v);
+    if (++st == LNS_STAGES) { st = 0; ph ^= 1; }
+  }
+}
+
+int g_ln_staged = 1;   // dwm_b200_set_option("ln_staged", 0 | 1)
+
+template <typename T, int VPL, bool DUAL>
+static int launch_ln_staged(const LnParams& p, cudaStream_t s) {
+  const int n_groups = (p.M + LNS_ROWS - 1) / LNS_ROWS;
+  const int smem = LNS_STAGES * LNS_ROWS * p.D * 4 + 2 * LNS_STAGES * 8;
+  const int grid = n_groups < sm_count() ? n_groups : sm_count();
+  const bool exact = (p.D >> 2) == 32 * VPL;
+  auto go = [&](auto kern) -> int {
+    DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, LNS_THREADS, smem, s>>>(p, n_groups);
+    DWM_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  };
+  return exact ? go(layernorm_staged_kernel<T, VPL, DUAL, true>) : go(layernorm_staged_kernel<T, VPL, DUAL, false>);
+}
+
 template <typename T, bool DUAL>
 static int launch_ln2(const LnParams& p, cudaStream_t s) {
   const int need = (p.D / 4 + 31) / 32;
+  // staged path: no per-row residual input, rows 16-byte aligned, ring <= 200 KB, enough rows
+  const bool staged = g_ln_staged && !p.add_full && (p.ldx & 3) == 0 && p.D <= 2048 && p.M >= 4096 &&
+                      (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
+  if (staged) {
+    if (need <= 3) return launch_ln_staged<T, 3, DUAL>(p, s);
+    if (need <= 6) return launch_ln_staged<T, 6, DUAL>(p, s);
+    if (need <= 12) return launch_ln_staged<T, 12, DUAL>(p, s);
+    return launch_ln_staged<T, 16, DUAL>(p, s);
+  }
   const unsigned grid = static_cast<unsigned>((p.M + LN_WARPS - 1) / LN_WARPS);
   const int threads = LN_WARPS * 32;
   if (need <= 3) layernorm_kernel<T, 3, DUAL><<<grid, threads, 0, s>>>(p);

@@ -134,65 +134,72 @@ struct SnParams {
   void* out; int out_T, out_t0;
 };
 
+// grid = (chunks, nb): a block works on SN_CHUNK float4 of ONE image, so the (mean, rstd) of its
+// G groups are finalised once per block from the fp64 sums (first G threads, shared memory)
+// instead of per thread — the fp64 divisions made the per-thread version XU-pipe bound.
+constexpr int SN_CHUNK = 4096;
+
 template <typename T>
 __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
+  __shared__ float2 s_stat[64];
   const int vec = p.C >> 2;
-  const long long total = static_cast<long long>(p.nb) * p.T * p.H * p.W * vec;
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c4 = static_cast<int>(i % vec);
-  long long r = i / vec;
-  const int w = static_cast<int>(r % p.W); r /= p.W;
-  const int h = static_cast<int>(r % p.H); r /= p.H;
-  const int t = static_cast<int>(r % p.T);
-  const int n = static_cast<int>(r / p.T);
+  const int n = blockIdx.y;
   const int cg = p.C / p.G;
-  const double cnt = static_cast<double>(cg) * p.T * p.H * p.W;
-  auto stats = [&](int g, float& mean, float& rstd) {
-    const double s = p.sums[(static_cast<long long>(n) * p.G + g) * 2];
-    const double ss = p.sums[(static_cast<long long>(n) * p.G + g) * 2 + 1];
+  const long long per_img = static_cast<long long>(p.T) * p.H * p.W * vec;
+  if (threadIdx.x < p.G) {
+    const double cnt = static_cast<double>(cg) * p.T * p.H * p.W;
+    const double s = p.sums[(static_cast<long long>(n) * p.G + threadIdx.x) * 2];
+    const double ss = p.sums[(static_cast<long long>(n) * p.G + threadIdx.x) * 2 + 1];
     const double mean_d = s / cnt;
-    mean = static_cast<float>(mean_d);
-    rstd = rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps);
-  };
-  float4 v = reinterpret_cast<const float4*>(p.x)[i];
-  const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
-  const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
-  if ((cg & 3) == 0) {
-    float mean, rstd;
-    stats((c4 * 4) / cg, mean, rstd);
-    v.x = (v.x - mean) * rstd * ga.x + be.x;
-    v.y = (v.y - mean) * rstd * ga.y + be.y;
-    v.z = (v.z - mean) * rstd * ga.z + be.z;
-    v.w = (v.w - mean) * rstd * ga.w + be.w;
-  } else {   // a float4 may straddle groups (e.g. 10 or 2 channels per group): per-element statistics
-    float* ve = reinterpret_cast<float*>(&v);
-    const float* gae = reinterpret_cast<const float*>(&ga);
-    const float* bee = reinterpret_cast<const float*>(&be);
-    int g_prev = -1;
-    float mean = 0.f, rstd = 0.f;
+    s_stat[threadIdx.x] = make_float2(static_cast<float>(mean_d),
+                                      rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps));
+  }
+  __syncthreads();
+  const long long i0 = static_cast<long long>(blockIdx.x) * SN_CHUNK;
+  long long i1 = i0 + SN_CHUNK;
+  if (i1 > per_img) i1 = per_img;
+  const float4* xin = reinterpret_cast<const float4*>(p.x) + static_cast<long long>(n) * per_img;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int c4 = static_cast<int>(i % vec);
+    long long r = i / vec;
+    const int w = static_cast<int>(r % p.W); r /= p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int t = static_cast<int>(r / p.H);
+    float4 v = xin[i];
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+    if ((cg & 3) == 0) {
+      const float2 st = s_stat[(c4 * 4) / cg];
+      v.x = (v.x - st.x) * st.y * ga.x + be.x;
+      v.y = (v.y - st.x) * st.y * ga.y + be.y;
+      v.z = (v.z - st.x) * st.y * ga.z + be.z;
+      v.w = (v.w - st.x) * st.y * ga.w + be.w;
+    } else {   // a float4 may straddle groups (e.g. 10 or 2 channels per group)
+      float* ve = reinterpret_cast<float*>(&v);
+      const float* gae = reinterpret_cast<const float*>(&ga);
+      const float* bee = reinterpret_cast<const float*>(&be);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int g = (c4 * 4 + e) / cg;
-      if (g != g_prev) { stats(g, mean, rstd); g_prev = g; }
-      ve[e] = (ve[e] - mean) * rstd * gae[e] + bee[e];
+      for (int e = 0; e < 4; ++e) {
+        const float2 st = s_stat[(c4 * 4 + e) / cg];
+        ve[e] = (ve[e] - st.x) * st.y * gae[e] + bee[e];
+      }
     }
+    if (p.zy) {
+      // nearest-neighbour position in the latent grid; odd T > 1 treats the first frame apart
+      int tz;
+      if (p.T > 1 && (p.T & 1)) tz = t == 0 ? 0 : 1 + ((t - 1) * (p.Tz - 1)) / (p.T - 1);
+      else tz = (t * p.Tz) / p.T;
+      const int hq = (h * p.hz) / p.H, wq = (w * p.wz) / p.W;
+      const long long zi = (((static_cast<long long>(n) * p.Tz + tz) * p.hz + hq) * p.wz + wq) * vec + c4;
+      const float4 y = __ldg(reinterpret_cast<const float4*>(p.zy) + zi);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.zb) + zi);
+      v.x = v.x * y.x + b.x; v.y = v.y * y.y + b.y; v.z = v.z * y.z + b.z; v.w = v.w * y.w + b.w;
+    }
+    if (p.silu) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+    const long long o = (((static_cast<long long>(n) * p.out_T + p.out_t0 + t) * p.H + h) * p.W + w) * vec + c4;
+    uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
+    reinterpret_cast<uint2*>(p.out)[o] = pk;
   }
-  if (p.zy) {
-    // nearest-neighbour position in the latent grid; odd T > 1 treats the first frame apart
-    int tz;
-    if (p.T > 1 && (p.T & 1)) tz = t == 0 ? 0 : 1 + ((t - 1) * (p.Tz - 1)) / (p.T - 1);
-    else tz = (t * p.Tz) / p.T;
-    const int hq = (h * p.hz) / p.H, wq = (w * p.wz) / p.W;
-    const long long zi = (((static_cast<long long>(n) * p.Tz + tz) * p.hz + hq) * p.wz + wq) * vec + c4;
-    const float4 y = __ldg(reinterpret_cast<const float4*>(p.zy) + zi);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.zb) + zi);
-    v.x = v.x * y.x + b.x; v.y = v.y * y.y + b.y; v.z = v.z * y.z + b.z; v.w = v.w * y.w + b.w;
-  }
-  if (p.silu) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
-  const long long o = (((static_cast<long long>(n) * p.out_T + p.out_t0 + t) * p.H + h) * p.W + w) * vec + c4;
-  uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
-  reinterpret_cast<uint2*>(p.out)[o] = pk;
 }
 
 // ---- nearest upsample x2 in space, optionally in time (CogVideoXUpsample3D rules) ----
@@ -270,8 +277,9 @@ extern "C" int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, 
   p.x = x; p.nb = (int)nb; p.T = (int)T; p.H = (int)H; p.W = (int)W; p.C = C; p.G = groups;
   p.sums = sums; p.eps = eps; p.gamma = gamma; p.beta = beta; p.zy = zy; p.zb = zb;
   p.Tz = Tz; p.hz = hz; p.wz = wz; p.silu = apply_silu; p.out = out; p.out_T = (int)out_T; p.out_t0 = (int)out_t0;
-  const long long total = nb * T * H * W * (C / 4);
-  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  DWM_REQUIRE(groups <= 64 && nb <= 65535, "dwm_b200_spatialnorm_silu: groups <= 64 and nb <= 65535 required");
+  const long long per_img = T * H * W * (C / 4);
+  dim3 grid(static_cast<unsigned>((per_img + SN_CHUNK - 1) / SN_CHUNK), static_cast<unsigned>(nb));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == DWM_BF16) spatialnorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
   else if (dtype == DWM_F16) spatialnorm_kernel<__half><<<grid, 256, 0, s>>>(p);

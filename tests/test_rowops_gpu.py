@@ -48,6 +48,55 @@ def test_layernorm_dual_modulation():
     assert ((o2.float() - r2).abs().max() / r2.abs().max()).item() < 6e-3
 
 
+@pytest.mark.parametrize("D,items,S,variant", [
+    (1536, 13, 448, "mod"),          # exact vector count, item changes inside row groups
+    (1536, 11, 397, "dual"),         # ragged last group (M % 8 != 0)
+    (320, 41, 101, "affine_item"),   # D/4 = 80: bounds-checked vectors, small rows
+    (1280, 9, 500, "affine_item"),
+    (2048, 5, 1000, "mod"),
+])
+@pytest.mark.parametrize("staged", [1, 0])
+def test_layernorm_large_m_staged_and_resident(D, items, S, variant, staged):
+    """M >= 4096 rows take the bulk-copy staged kernel (ln_staged = 1); both kernels must give
+    bit-identical results (same per-row arithmetic) and match torch."""
+    from opendwm_b200 import ops, lib
+    M = items * S
+    xbuf = _r((M, D + 64), 1) * 2 + 0.3
+    x = xbuf[:, :D]                                            # row pitch != D
+    out = torch.empty(M, D, dtype=torch.bfloat16, device="cuda")
+    lib.set_option("ln_staged", staged)
+    try:
+        if variant == "affine_item":
+            emb = _r((items, D), 2)
+            w, b = _r((D,), 4) * 0.1 + 1, _r((D,), 5) * 0.1
+            ssum = torch.empty(M, D, device="cuda")
+            ops.layernorm(x, out, weight=w, bias=b, eps=1e-5, add_item=emb, rows_per_item=S,
+                          sum_out=ssum)
+            t = x + emb.repeat_interleave(S, 0)
+            assert torch.equal(ssum, t)
+            ref = torch.nn.functional.layer_norm(t, (D,), w, b, 1e-5)
+            outs, refs = [out], [ref]
+        else:
+            mod = _r((items, 9 * D), 2) * 0.3
+            sh, sc = mod[:, :D], mod[:, D:2 * D]
+            n = torch.nn.functional.layer_norm(x, (D,), None, None, 1e-6)
+            refs = [n * (1 + sc.repeat_interleave(S, 0)) + sh.repeat_interleave(S, 0)]
+            outs = [out]
+            if variant == "dual":
+                sh2, sc2 = mod[:, 6 * D:7 * D], mod[:, 7 * D:8 * D]
+                o2 = torch.empty_like(out)
+                ops.layernorm(x, out, eps=1e-6, rows_per_item=S, shift=sh, scale=sc, shift2=sh2,
+                              scale2=sc2, out2=o2)
+                outs.append(o2)
+                refs.append(n * (1 + sc2.repeat_interleave(S, 0)) + sh2.repeat_interleave(S, 0))
+            else:
+                ops.layernorm(x, out, eps=1e-6, rows_per_item=S, shift=sh, scale=sc)
+    finally:
+        lib.set_option("ln_staged", 1)
+    for o, r in zip(outs, refs):
+        assert ((o.float() - r).abs().max() / r.abs().max()).item() < 6e-3
+
+
 def test_act_cast_and_sinusoid():
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

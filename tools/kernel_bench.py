@@ -54,8 +54,11 @@ def main():
     a16 = torch.empty(N * S, D, device="cuda", dtype=dt)
     mod = torch.randn(N, 6 * D, device="cuda")
     f = lambda: ops.layernorm(x, a16, eps=1e-6, rows_per_item=S, shift=mod[:, :D], scale=mod[:, D:2 * D])
-    t = timeit(f)
-    res["layernorm_mod"] = dict(ms=t, gbs=(x.numel() * 4 + a16.numel() * 2) / t / 1e6)
+    for staged, tag in ((1, ""), (0, "_resident")):
+        lib.set_option("ln_staged", staged)
+        t = timeit(f)
+        res["layernorm_mod" + tag] = dict(ms=t, gbs=(x.numel() * 4 + a16.numel() * 2) / t / 1e6)
+    lib.set_option("ln_staged", 1)
     w, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
     y = torch.empty_like(x)
     emb = torch.randn(N, D, device="cuda")
