@@ -145,11 +145,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) layernorm_kernel(const LnParams
   ln_finish<T, VPL, DUAL, false>(p, m, lane, v);
 }
 
-// Staged variant: a producer thread streams groups of 8 rows into a 3-stage shared-memory ring
-// with 1-D bulk copies (cp.async.bulk + mbarrier transaction counts); 8 compute warps take
-// one row each.  Memory-level parallelism (72-144 KB in flight per SM) no longer depends on
+// Staged variant: a producer thread streams groups of 16 rows into a 2-stage shared-memory ring
+// with 1-D bulk copies (cp.async.bulk + mbarrier transaction counts); 16 compute warps take
+// one row each.  Memory-level parallelism (96-192 KB in flight per SM) no longer depends on
 // occupancy — the register-resident kernel above stalls on long_scoreboard at 31 % occupancy.
-constexpr int LNS_ROWS = 8, LNS_STAGES = 3, LNS_THREADS = (LNS_ROWS + 1) * 32;
+constexpr int LNS_ROWS = 16, LNS_STAGES = 2, LNS_THREADS = (LNS_ROWS + 1) * 32;
 
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -227,8 +227,9 @@ static int launch_ln_staged(const LnParams& p, cudaStream_t s) {
 template <typename T, bool DUAL>
 static int launch_ln2(const LnParams& p, cudaStream_t s) {
   const int need = (p.D / 4 + 31) / 32;
-  // staged path: no per-row residual input, rows 16-byte aligned, ring <= 200 KB, enough rows
-  const bool staged = g_ln_staged && !p.add_full && (p.ldx & 3) == 0 && p.D <= 2048 && p.M >= 4096 &&
+  // staged path: no per-row residual input, rows 16-byte aligned, ring <= 220 KB, enough rows
+  const bool staged = g_ln_staged && !p.add_full && (p.ldx & 3) == 0 &&
+                      LNS_STAGES * LNS_ROWS * p.D * 4 <= 220 * 1024 && p.M >= 4096 &&
                       (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
   if (staged) {
     if (need <= 3) return launch_ln_staged<T, 3, DUAL>(p, s);
