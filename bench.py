@@ -483,42 +483,59 @@ def run_reference(args):
     B, T, V, C, H, W = cfg["latent_shape"]
     mcfg = dict(cfg["model"])
     t0 = time.perf_counter()
-    with torch.device("meta"):
-        model = octsd.DiTCrossviewTemporalConditionModel(**mcfg)
-    model = model.to_empty(device="cpu").eval()
-    pattern = torch.randn(1 << 22, generator=torch.Generator().manual_seed(0)) * 0.02
+    # Build cost only (not timed work): the sin/cos position table is zeroed below anyway, so
+    # its 38 s float64 numpy evaluation is skipped; the large weights are views into ONE
+    # 128 MB N(0, 0.02) buffer instead of 15 GB of first-touch pages (this can only favour
+    # the CPU arm: its weights stay cache-resident).
+    import numpy as np
+    from oracle import d31
+    real_sincos = d31.get_2d_sincos_pos_embed
+    d31.get_2d_sincos_pos_embed = lambda dim, grid, **kw: np.zeros((grid * grid, dim), np.float32)
+    try:
+        with torch.device("meta"):
+            model = octsd.DiTCrossviewTemporalConditionModel(**mcfg)
+    finally:
+        d31.get_2d_sincos_pos_embed = real_sincos
+    pattern = torch.randn(1 << 25, generator=torch.Generator().manual_seed(0)) * 0.02
     with torch.no_grad():
-        for name, p in model.named_parameters():
-            if p.dim() == 1 and name.endswith(".weight"):
-                p.fill_(1.0)
-            elif name.endswith(".bias") or name.endswith("mix_factor"):
-                p.fill_(0.0)
-            else:                                # N(0, 0.02) pattern, tiled (fast init)
-                flat = p.view(-1)
-                n = flat.numel()
-                for s0 in range(0, n, pattern.numel()):
-                    m = min(pattern.numel(), n - s0)
-                    flat[s0:s0 + m] = pattern[:m]
-        pe = model.pos_embed.pos_embed
-        pe.copy_(torch.zeros_like(pe))
+        for mod in model.modules():
+            for name, p in list(mod._parameters.items()):
+                if p is None:
+                    continue
+                if p.dim() == 1 and name == "weight":
+                    new = torch.ones(p.shape)
+                elif name in ("bias", "mix_factor") or p.numel() > pattern.numel():
+                    new = torch.zeros(p.shape)
+                else:
+                    new = pattern[:p.numel()].view(p.shape)
+                mod._parameters[name] = torch.nn.Parameter(new, requires_grad=False)
+            for name, b in list(mod._buffers.items()):
+                if b is not None and b.is_meta:
+                    mod._buffers[name] = torch.zeros(b.shape, dtype=b.dtype)
+    model.eval()
     t_build = time.perf_counter() - t0
     Ts, items = 1, V
     cond = synthetic_conditions(cfg, 1, Ts, V, "cpu", torch.float32)
     sample = torch.randn(1, Ts, V, C, H, W)
     timestep = torch.full((1, Ts, V), 500.0)
     times = []
+    budget_s = 150.0           # bounded: at most 1 warm-up + as many of K samples as fit
+    t_loop = time.perf_counter()
     with torch.no_grad():
-        for k in range(args.warmup + args.steps):
+        for k in range(min(args.warmup, 1) + args.steps):
             t0 = time.perf_counter()
             model(sample, timestep, **cond)
             dt = time.perf_counter() - t0
-            if k >= args.warmup:
+            if k >= min(args.warmup, 1):
                 times.append(dt)
+            if times and time.perf_counter() - t_loop + dt > budget_s:
+                break
     full_items = 2 * B * T * V
     ms = statistics.mean(times) * 1000.0 * full_items / items
     line = {
         "impl": "reference", "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ctsd_35 DFoT 6-view x 16-frame with layout",
@@ -527,8 +544,9 @@ def run_reference(args):
             "value": 1000.0 / ms, "unit": "steps/s", "cores": cores, "kind": "port",
             "sample": "oracle fp32 full-depth DiT forward incl. ImageAdapter on 1 frame x "
                       "%d views (no CFG) = %d of %d view-frame items per timed step, "
-                      "scaled x%d; model build %.0f s" % (V, items, full_items,
-                                                          full_items // items, t_build)},
+                      "scaled x%d; %d timed samples within a %d s budget; model build %.0f s"
+                      % (V, items, full_items, full_items // items, len(times), int(budget_s),
+                         t_build)},
         "e2e": {"value": 1000.0 / ms, "unit": "steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
