@@ -2,7 +2,16 @@
 
 fp32 PyTorch restatement of OpenDWM's own CTSD code on the denoising hot path,
 each function citing the reference file:line it follows.  Built on oracle/d31.py
-for the diffusers pieces.  PARITY UNPINNED (see oracle/d31.py header).
+for the diffusers pieces.
+
+PINNED AGAINST THE REFERENCE'S OWN CODE for everything restated in THIS file:
+tests/golden/make_reference_golden.py imports /root/reference/src/dwm
+(crossview_temporal_dit.py, crossview_temporal.py, adapters.py,
+schedulers/temporal_independent.py) on a name-mapping shim that resolves `diffusers.*` to
+oracle/d31.py, runs nine DiT configurations and the three schedulers, and
+tests/test_reference_golden.py checks this module against those outputs (bit-exact on the
+build host).  The diffusers-side arithmetic underneath (oracle/d31.py) stays PARITY
+UNPINNED (see its header).
 """
 import torch
 from torch import nn

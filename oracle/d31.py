@@ -9,7 +9,10 @@ anchored on the reference's own call sites (cited per class).
 PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
 this path and cannot be imported here, so this oracle is
 checked for internal consistency only.  Parameter names follow the diffusers
-state_dict keys so real checkpoints load unchanged.
+state_dict keys so real checkpoints load unchanged.  (These classes
+also back the `diffusers` name shim under tests/golden/diffusers_stub, on which the
+reference's OWN modules are imported and run to pin oracle/ctsd.py — that pins the OpenDWM
+code paths, not the arithmetic of this file.)
 """
 import math
 

@@ -60,3 +60,57 @@ def synthetic_inputs(cfg, B=2, T=4, V=3, H=8, W=12, L=10, seed=0, device="cpu"):
     timestep = torch.rand(B, T, V, generator=g) * 1000
     mv = lambda t: t.to(device)
     return mv(sample), mv(timestep), {k: mv(v) for k, v in cond.items()}
+
+
+# -- cases shared by tests/golden/make_reference_golden.py (which runs the REFERENCE's own code
+#    on them) and the tests that check the oracle / the CUDA path against those fixtures --------
+
+VARIANTS = ["base", "temporal_rowwise", "temporal_full", "crossview_full", "no_adapter",
+            "no_qknorm_extra", "disabled_batch1", "no_perspective", "five_dim"]
+
+
+def variant_case(name):
+    """-> (cfg, sample, timestep, cond, forward kwargs); shared with the test."""
+    cfg = dict(TINY)
+    extra = {}
+    if name == "temporal_rowwise":
+        cfg["temporal_attention_type"] = "rowwise"
+    elif name == "temporal_full":
+        cfg["temporal_attention_type"] = "full"
+    elif name == "crossview_full":
+        cfg["crossview_attention_type"] = "full"
+    elif name == "no_adapter":
+        cfg["condition_image_adapter_config"] = None
+    elif name == "no_qknorm_extra":
+        cfg["qk_norm_on_additional_modules"] = None
+    elif name == "no_perspective":
+        cfg["perspective_modeling_type"] = ""
+    elif name == "five_dim":
+        cfg.update(enable_crossview=False, crossview_block_layers=None,
+                   perspective_modeling_type="", condition_image_adapter_config=None)
+    if name == "five_dim":
+        sample, timestep, cond = synthetic_inputs(cfg, V=1)
+        sample, timestep = sample.squeeze(2), timestep.squeeze(2)
+        cond = dict(encoder_hidden_states=cond["encoder_hidden_states"].squeeze(2),
+                    pooled_projections=cond["pooled_projections"].squeeze(2),
+                    disable_temporal=cond["disable_temporal"].unsqueeze(1))
+        extra["return_dict"] = True
+    else:
+        sample, timestep, cond = synthetic_inputs(cfg)
+        if name == "crossview_full":
+            cond["crossview_attention_mask"] = None
+        if name == "disabled_batch1":
+            cond["disable_temporal"] = torch.tensor([False, True])
+            cond["disable_crossview"] = torch.tensor([True, False])
+    return cfg, sample, timestep, cond, extra
+
+
+def scheduler_inputs():
+    g = torch.Generator().manual_seed(11)
+    shape = (2, 4, 3, 4, 6, 5)
+    return dict(
+        sample=torch.randn(shape, generator=g), model_output=torch.randn(shape, generator=g),
+        noise=torch.randn(shape, generator=g),
+        fm_indices=torch.randint(0, 12, shape[:3], generator=g),
+        ddim_timesteps=(torch.randint(0, 50, shape[:3], generator=g) * 20 + 1),
+        ddpm_timesteps=torch.randint(0, 1000, shape[:3], generator=g))

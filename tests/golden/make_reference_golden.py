@@ -1,0 +1,91 @@
+"""Generates `tests/golden/reference_*.safetensors` by RUNNING THE REFERENCE'S OWN CODE.
+
+Only works in the build container (needs /root/reference; nothing at test time does).
+`diffusers` is not installable offline, so the reference modules are imported on top of the
+name-mapping shim in tests/golden/diffusers_stub (every `diffusers.*` name the CTSD path
+touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/reference/src:
+
+  dwm/models/crossview_temporal_dit.py   DiTCrossviewTemporalConditionModel (forward, both
+                                         graft helpers, embeddings, un-patchify)
+  dwm/models/crossview_temporal.py       VTSelfAttentionBlock, AlphaBlender, Mixer
+  dwm/models/adapters.py                 ImageAdapter
+  dwm/schedulers/temporal_independent.py FlowMatchEulerDiscreteScheduler.step_by_indices,
+                                         DDIMScheduler.step, DDPMScheduler.add_noise /
+                                         get_velocity (tensor timesteps)
+
+The fixtures hold the reference outputs for seeded weights / inputs that the tests rebuild
+deterministically (tests/common.py).  tests/test_reference_golden_cpu.py checks the oracle
+restatement against them (bit-exact on the build host; 1e-6 elsewhere), which pins the
+oracle's restatement of OpenDWM's own code.  Usage:  python tests/golden/make_reference_golden.py
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/src"
+# order matters: the reference's `dwm`, not this repo's src/dwm mirror
+sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(ROOT, "tests")]
+
+import torch  # noqa: E402
+
+from common import (VARIANTS, scheduler_inputs, seeded_oracle,  # noqa: E402
+                    variant_case)
+
+def main():
+    import safetensors.torch
+    import dwm.models.crossview_temporal_dit as ref_dit
+    import dwm.schedulers.temporal_independent as ref_sched
+    assert ref_dit.__file__.startswith(REF), ref_dit.__file__
+    torch.set_num_threads(1)                      # deterministic reduction order
+    out, report = {}, {}
+    for name in VARIANTS:
+        cfg, sample, timestep, cond, extra = variant_case(name)
+        oracle = seeded_oracle(cfg)
+        ref = ref_dit.DiTCrossviewTemporalConditionModel(**cfg)
+        missing, unexpected = ref.load_state_dict(oracle.state_dict(), strict=True)
+        assert not missing and not unexpected
+        ref.eval()
+        with torch.no_grad():
+            yr = ref(sample, timestep, **cond, **extra)
+            yo = oracle(sample, timestep, **cond, **extra)
+        yr = yr["noise_pred"] if extra else yr[0][0]
+        yo = yo["noise_pred"] if extra else yo[0][0]
+        out["dit_" + name] = yr.contiguous()
+        report["dit_" + name] = {"shape": list(yr.shape), "absmax": yr.abs().max().item(),
+                                 "oracle_max_abs_diff": (yr - yo).abs().max().item()}
+
+    si = scheduler_inputs()
+    fm = ref_sched.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=3.0)
+    fm.set_timesteps(12)
+    out["fm_sigmas"] = fm.sigmas.clone()
+    out["fm_timesteps"] = fm.timesteps.clone()
+    out["fm_step_by_indices"] = fm.step_by_indices(
+        si["model_output"], si["fm_indices"], si["sample"], return_dict=False)[0].contiguous()
+    sd21 = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
+                steps_offset=1)
+    for pt in ("v_prediction", "epsilon", "sample"):
+        ddim = ref_sched.DDIMScheduler(prediction_type=pt, **sd21)
+        ddim.set_timesteps(50)
+        out["ddim_step_" + pt] = ddim.step(
+            si["model_output"], si["ddim_timesteps"], si["sample"],
+            return_dict=False)[0].contiguous()
+    out["ddim_timesteps_50"] = ddim.timesteps.clone()
+    ddpm = ref_sched.DDPMScheduler(prediction_type="v_prediction", **sd21)
+    out["ddpm_add_noise"] = ddpm.add_noise(si["sample"], si["noise"], si["ddpm_timesteps"]).contiguous()
+    out["ddpm_get_velocity"] = ddpm.get_velocity(
+        si["sample"], si["noise"], si["ddpm_timesteps"]).contiguous()
+
+    safetensors.torch.save_file(out, os.path.join(HERE, "reference_outputs.safetensors"))
+    with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
+        json.dump({"generated_from": "/root/reference/src (OpenDWM @ b0ecc3d) on the "
+                                     "diffusers shim tests/golden/diffusers_stub",
+                   "torch": torch.__version__, "cases": report}, f, indent=1)
+    for k, v in report.items():
+        print(k, v)
+
+
+if __name__ == "__main__":
+    main()
