@@ -64,4 +64,30 @@ class SD3Transformer2DModel(ModelMixin):
 
 
 class UNetSpatioTemporalConditionModel(ModelMixin):
-    """Only the name (isinstance checks); the UNet family is pinned through oracle/unet.py."""
+    """What the reference keeps of diffusers 0.31 UNetSpatioTemporalConditionModel after
+    its positional super().__init__ (/root/reference/src/dwm/models/crossview_temporal_unet.py
+    :407-418): input / output convolutions and the time / added-time embeddings.  The
+    down / mid / up blocks built by the stock class are replaced by the reference at once
+    and are therefore not constructed here."""
+
+    @register_to_config
+    def __init__(self, sample_size=None, in_channels=8, out_channels=4, down_block_types=(),
+                 up_block_types=(), block_out_channels=(320, 640, 1280, 1280),
+                 addition_time_embed_dim=256, projection_class_embeddings_input_dim=768,
+                 layers_per_block=2, cross_attention_dim=1024, transformer_layers_per_block=1,
+                 num_attention_heads=(5, 10, 20, 20), num_frames=25):
+        super().__init__()
+        boc = block_out_channels
+        time_embed_dim = boc[0] * 4
+        self.conv_in = nn.Conv2d(in_channels, boc[0], kernel_size=3, padding=1)
+        self.time_proj = d31.Timesteps(boc[0], True, 0)
+        self.time_embedding = d31.TimestepEmbedding(boc[0], time_embed_dim)
+        self.add_time_proj = d31.Timesteps(addition_time_embed_dim, True, 0)
+        self.add_embedding = d31.TimestepEmbedding(projection_class_embeddings_input_dim,
+                                                   time_embed_dim)
+        self.down_blocks = nn.ModuleList([])
+        self.up_blocks = nn.ModuleList([])
+        self.mid_block = None
+        self.conv_norm_out = nn.GroupNorm(num_channels=boc[0], num_groups=32, eps=1e-5)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(boc[0], out_channels, kernel_size=3, padding=1)

@@ -9,6 +9,9 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
                                          graft helpers, embeddings, un-patchify)
   dwm/models/crossview_temporal.py       VTSelfAttentionBlock, AlphaBlender, Mixer
   dwm/models/adapters.py                 ImageAdapter
+  dwm/models/crossview_temporal_unet.py  UNetCrossviewTemporalConditionModel + its five block
+                                         classes; crossview_temporal.py ResBlock,
+                                         TransformerModel, TemporalBasicTransformerBlock
   dwm/schedulers/temporal_independent.py FlowMatchEulerDiscreteScheduler.step_by_indices,
                                          DDIMScheduler.step, DDPMScheduler.add_noise /
                                          get_velocity (tensor timesteps)
@@ -55,6 +58,23 @@ def main():
         out["dit_" + name] = yr.contiguous()
         report["dit_" + name] = {"shape": list(yr.shape), "absmax": yr.abs().max().item(),
                                  "oracle_max_abs_diff": (yr - yo).abs().max().item()}
+
+    import dwm.models.crossview_temporal_unet as ref_unet
+    from test_unet import UNET_CASES, _oracle as unet_oracle, unet_case
+    assert ref_unet.__file__.startswith(REF), ref_unet.__file__
+    for B, T, V, variant in UNET_CASES:
+        cfg, x, t, c = unet_case(B, T, V, variant)
+        oracle = unet_oracle(cfg)
+        ref = ref_unet.UNetCrossviewTemporalConditionModel(**cfg)
+        missing, unexpected = ref.load_state_dict(oracle.state_dict(), strict=True)
+        assert not missing and not unexpected
+        ref.eval()
+        with torch.no_grad():
+            yr = ref(x, t, **c)[0][0]
+            yo = oracle(x, t, **c)[0]
+        out["unet_" + variant] = yr.contiguous()
+        report["unet_" + variant] = {"shape": list(yr.shape), "absmax": yr.abs().max().item(),
+                                     "oracle_max_abs_diff": (yr - yo).abs().max().item()}
 
     si = scheduler_inputs()
     fm = ref_sched.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=3.0)

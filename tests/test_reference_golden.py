@@ -42,6 +42,23 @@ def test_oracle_dit_matches_reference(name, golden):
     assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
 
 
+def _unet_cases():
+    from test_unet import UNET_CASES
+    return UNET_CASES
+
+
+@pytest.mark.parametrize("B,T,V,variant", _unet_cases())
+def test_oracle_unet_matches_reference(B, T, V, variant, golden):
+    from test_unet import _oracle, unet_case
+    torch.set_num_threads(1)
+    cfg, x, t, c = unet_case(B, T, V, variant)
+    with torch.no_grad():
+        y = _oracle(cfg)(x, t, **c)[0]
+    ref = golden["unet_" + variant]
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
 def test_oracle_schedulers_match_reference(golden):
     from oracle import ctsd as octsd
     si = scheduler_inputs()
@@ -94,6 +111,20 @@ def test_cuda_dit_matches_reference(name, golden):
     y = m(sample.cuda(), timestep.cuda(), **cond, **extra)
     y = y["noise_pred"] if extra else y[0][0]
     assert _rel(y.cpu(), golden["dit_" + name]) < 4e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,variant", _unet_cases())
+def test_cuda_unet_matches_reference(B, T, V, variant, golden):
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+    from test_unet import _oracle, unet_case
+    cfg, x, t, c = unet_case(B, T, V, variant)
+    m = U(**cfg, compute_dtype=torch.float16)
+    m.load_state_dict(_oracle(cfg).state_dict())
+    m.cuda()
+    c = {k: (v.cuda() if v is not None else None) for k, v in c.items()}
+    y = m(x.cuda(), t.cuda(), **c)[0][0]
+    assert _rel(y.cpu(), golden["unet_" + variant]) < 6e-3
 
 
 @pytest.mark.gpu

@@ -67,24 +67,33 @@ def test_state_dict_and_renamer_cpu():
         m(x, t, **c)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("B,T,V,variant", [(2, 1, 3, "image"), (2, 3, 2, "video"),
-                                           (1, 2, 4, "pointwise"), (2, 2, 2, "disabled")])
-def test_unet_forward_matches_oracle(B, T, V, variant):
-    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+UNET_CASES = [(2, 1, 3, "image"), (2, 3, 2, "video"), (1, 2, 4, "pointwise"),
+              (2, 2, 2, "disabled")]
+
+
+def unet_case(B, T, V, variant):
+    """-> (cfg, sample, timesteps, cond); shared with tests/golden/make_reference_golden.py."""
     cfg = dict(UCFG)
     if variant == "pointwise":
         cfg.update(enable_rowwise_crossview=False, enable_rowwise_temporal=False)
-    o = _oracle(cfg).cuda()
-    m = U(**cfg, compute_dtype=torch.float16)
-    m.load_state_dict(o.state_dict())
-    m.cuda()
     x, t, c = _inputs(B, T, V)
     if variant == "pointwise":
         c["crossview_attention_mask"] = None
     if variant == "disabled":
         c["disable_temporal"] = torch.tensor([True, True])
         c["disable_crossview"] = torch.tensor([True, False])
+    return cfg, x, t, c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,V,variant", UNET_CASES)
+def test_unet_forward_matches_oracle(B, T, V, variant):
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+    cfg, x, t, c = unet_case(B, T, V, variant)
+    o = _oracle(cfg).cuda()
+    m = U(**cfg, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    m.cuda()
     x, t = x.cuda(), t.cuda()
     c = {k: (v.cuda() if v is not None else None) for k, v in c.items()}
     with torch.no_grad():
