@@ -8,7 +8,8 @@ PINNED AGAINST THE REFERENCE'S OWN CODE for everything restated in THIS file:
 tests/golden/make_reference_golden.py imports /root/reference/src/dwm
 (crossview_temporal_dit.py, crossview_temporal.py, adapters.py,
 schedulers/temporal_independent.py) on a name-mapping shim that resolves `diffusers.*` to
-oracle/d31.py, runs nine DiT configurations and the three schedulers, and
+oracle/d31.py, runs nine DiT configurations, the three schedulers and three iterations of
+the reference's StreamingCrossviewTemporalSD.inference_pipeline loop, and
 tests/test_reference_golden.py checks this module against those outputs (bit-exact on the
 build host).  The diffusers-side arithmetic underneath (oracle/d31.py) stays PARITY
 UNPINNED (see its header).

@@ -7,7 +7,16 @@ src/dwm/models/crossview_temporal.py (ResBlock :75-164, TemporalBasicTransformer
 diffusers==0.31.0 pieces they inherit (ResnetBlock2D, TemporalResnetBlock,
 BasicTransformerBlock, Downsample2D, Upsample2D, UNetSpatioTemporalConditionModel
 members).  Parameter names follow the reference state_dict
-(Appendix B).  PARITY UNPINNED (see oracle/d31.py header).
+(Appendix B).
+
+PINNED AGAINST THE REFERENCE'S OWN CODE for what this file restates of OpenDWM
+(ResBlock, TemporalBasicTransformerBlock, TransformerModel, the five block classes and the
+model forward): tests/golden/make_reference_golden.py runs the reference's
+UNetCrossviewTemporalConditionModel from /root/reference/src on the diffusers name shim
+(tests/golden/diffusers_stub) in four configurations and this module reproduces the outputs
+bit-exactly (tests/test_reference_golden.py).  The restated diffusers blocks in here
+(ResnetBlock2D, TemporalResnetBlock, BasicTransformerBlock, samplers) also BACK that shim,
+so their arithmetic stays PARITY UNPINNED (see oracle/d31.py header).
 """
 import einops
 import torch

@@ -114,3 +114,66 @@ def scheduler_inputs():
         fm_indices=torch.randint(0, 12, shape[:3], generator=g),
         ddim_timesteps=(torch.randint(0, 50, shape[:3], generator=g) * 20 + 1),
         ddpm_timesteps=torch.randint(0, 1000, shape[:3], generator=g))
+
+
+def _rigid(g, *lead, scale=1.0):
+    """Random rigid transforms [..., 4, 4] (rotation about z + translation)."""
+    ang = torch.randn(*lead, generator=g) * 0.2
+    t = torch.randn(*lead, 3, generator=g) * scale
+    m = torch.eye(4).repeat(*lead, 1, 1)
+    m[..., 0, 0], m[..., 0, 1] = torch.cos(ang), -torch.sin(ang)
+    m[..., 1, 0], m[..., 1, 1] = torch.sin(ang), torch.cos(ang)
+    m[..., :3, 3] = t
+    return m
+
+
+def condition_batch(T=4, V=3, L=10, seed=0, hw=(16, 24), text_dim=64, pooled_dim=32):
+    """A data batch with every key CrossviewTemporalSD.get_conditions reads (pre-encoded
+    text instead of prompts), non-trivial camera / ego matrices."""
+    g = torch.Generator().manual_seed(seed)
+    K = torch.zeros(1, T, V, 3, 3)
+    K[..., 0, 0] = 500 + 50 * torch.rand(1, T, V, generator=g)
+    K[..., 1, 1] = 500 + 50 * torch.rand(1, T, V, generator=g)
+    K[..., 0, 2], K[..., 1, 2], K[..., 2, 2] = hw[1] / 2, hw[0] / 2, 1.0
+    ego = _rigid(g, 1, 1, V + 2, scale=0.5).repeat(1, T, 1, 1, 1)
+    step = _rigid(g, 1, T, 1, scale=0.8)
+    pose = torch.eye(4).view(1, 1, 1, 4, 4).repeat(1, T, 1, 1, 1)
+    for t in range(1, T):
+        pose[:, t] = pose[:, t - 1] @ step[:, t]
+    ego = pose @ ego                                      # moving rig, [1, T, V + 2, 4, 4]
+    ring = torch.zeros(V, V, dtype=torch.bool)
+    for i in range(V):
+        for d in (-1, 0, 1):
+            ring[i, (i + d) % V] = True
+    return {
+        "pts": torch.arange(T).float().view(1, T, 1).repeat(1, 1, V) * 100,
+        "fps": torch.tensor([10.0]),
+        "text_embeddings": torch.randn(1, T, V, L, text_dim, generator=g) * 0.5,
+        "pooled_text_embeddings": torch.randn(1, T, V, pooled_dim, generator=g),
+        "3dbox_images": torch.rand(1, T, V, 3, *hw, generator=g),
+        "hdmap_images": torch.rand(1, T, V, 3, *hw, generator=g),
+        "crossview_mask": ring.unsqueeze(0),
+        "camera_intrinsics": K,
+        "camera_transforms": _rigid(g, 1, T, V, scale=1.5),
+        "image_size": torch.tensor([float(hw[1]), float(hw[0])]).expand(1, T, V, 2).clone(),
+        "ego_transforms": ego,
+    }
+
+
+CONDITION_COMMON = {
+    "frame_prediction_style": "diffusion_forcing", "condition_on_all_frames": True,
+    "uncondition_image_color": 0.1255, "added_time_ids": "fps_camera_transforms",
+    "camera_intrinsic_embedding_indices": [0, 4, 2, 5],
+    "camera_intrinsic_denom_embedding_indices": [1, 1, 0, 1],
+    "camera_transform_embedding_indices": [2, 6, 10, 3, 7, 11]}
+CONDITION_CASES = {
+    # name -> (common_config overrides, get_conditions kwargs)
+    "cfg": ({}, dict(do_classifier_free_guidance=True)),
+    "action_cfg": ({"added_time_ids": "fps_camera_transforms_action",
+                    "camera_ego_sensor_indices": [1, 2, 3]},
+                   dict(do_classifier_free_guidance=True)),
+    "masks_first_frame_only": ({"condition_on_all_frames": False, "disable_temporal": True},
+                               dict(do_classifier_free_guidance=False,
+                                    _3dbox_condition_mask=torch.tensor([[[True, False, True]]]),
+                                    hdmap_condition_mask=torch.tensor([[[False, True, True]]]))),
+}

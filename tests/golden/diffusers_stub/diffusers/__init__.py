@@ -19,7 +19,8 @@ from torch import nn
 
 from oracle import d31
 
-from . import configuration_utils, models, schedulers, utils  # noqa: F401
+from . import configuration_utils, image_processor, models, schedulers, utils  # noqa: F401
+from .schedulers import DDIMScheduler, DDPMScheduler, FlowMatchEulerDiscreteScheduler  # noqa: F401
 from .configuration_utils import register_to_config
 
 
@@ -91,3 +92,7 @@ class UNetSpatioTemporalConditionModel(ModelMixin):
         self.conv_norm_out = nn.GroupNorm(num_channels=boc[0], num_groups=32, eps=1e-5)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(boc[0], out_channels, kernel_size=3, padding=1)
+
+
+class AutoencoderKL:
+    """Name only (default of common_config["vae"], ctsd.py:953-954)."""

@@ -1,1 +1,1 @@
-from . import adapter, attention, attention_processor, embeddings, resnet, transformers, unets  # noqa: F401
+from . import adapter, autoencoders, attention, attention_processor, embeddings, resnet, transformers, unets  # noqa: F401

@@ -12,6 +12,10 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
   dwm/models/crossview_temporal_unet.py  UNetCrossviewTemporalConditionModel + its five block
                                          classes; crossview_temporal.py ResBlock,
                                          TransformerModel, TemporalBasicTransformerBlock
+  dwm/pipelines/ctsd.py                  StreamingCrossviewTemporalSD.reset_streaming +
+                                         inference_pipeline (the diffusion-forcing loop, 3
+                                         steps, CFG) and CrossviewTemporalSD.get_conditions /
+                                         get_camera_transform_ids / get_action_ids
   dwm/schedulers/temporal_independent.py FlowMatchEulerDiscreteScheduler.step_by_indices,
                                          DDIMScheduler.step, DDPMScheduler.add_noise /
                                          get_velocity (tensor timesteps)
@@ -33,7 +37,8 @@ sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(RO
 
 import torch  # noqa: E402
 
-from common import (VARIANTS, scheduler_inputs, seeded_oracle,  # noqa: E402
+from common import (CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS,  # noqa: E402
+                    condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
 def main():
@@ -75,6 +80,65 @@ def main():
         out["unet_" + variant] = yr.contiguous()
         report["unet_" + variant] = {"shape": list(yr.shape), "absmax": yr.abs().max().item(),
                                      "oracle_max_abs_diff": (yr - yo).abs().max().item()}
+
+    # ---- the reference's own diffusion-forcing loop and condition builder -------------------
+    import diffusers
+    import dwm.pipelines.ctsd as ref_pipe
+    from oracle import ctsd as octsd
+    assert ref_pipe.__file__.startswith(REF), ref_pipe.__file__
+    oracle = seeded_oracle(TINY)
+    ref = ref_dit.DiTCrossviewTemporalConditionModel(**TINY)
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    ref.eval()
+
+    class IdentityVae:                       # decode = identity: the loop's VAE call site runs
+        class config:
+            scaling_factor, shift_factor = 1.0, None
+        dtype = torch.float32
+
+        @staticmethod
+        def decode(x, return_dict=False):
+            return (x,)
+    pipe = object.__new__(ref_pipe.StreamingCrossviewTemporalSD)   # no checkpoints to load
+    pipe.common_config = {"frame_prediction_style": "diffusion_forcing"}
+    pipe.inference_config = {"guidance_scale": 2.0, "inference_steps": 12,
+                             "sequence_length_per_iteration": 4}
+    pipe.device, pipe.model_dtype = torch.device("cpu"), torch.float32
+    pipe.model = pipe.model_wrapper = ref
+    pipe.test_scheduler = ref_sched.FlowMatchEulerDiscreteScheduler(
+        num_train_timesteps=1000, shift=3.0)
+    pipe.vae, pipe.image_processor = IdentityVae(), diffusers.image_processor.VaeImageProcessor()
+    sample, _, cond = synthetic_inputs(TINY)
+    shape = (1, 4, 3, 16, 8, 12)
+    pipe.reset_streaming(shape, "pt")
+    pipe.conditions, pipe.latents = cond, sample[:1].clone()
+    with torch.no_grad():
+        lat = pipe.inference_pipeline(shape, start_timestep=9, stop_timestep=12)
+    sched = octsd.FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(12)
+    x = sample[:1].clone()
+    for i in (9, 10, 11):
+        x, _ = octsd.df_denoise_step(oracle, sched, x, cond, i=i, steps_per_inference=3,
+                                     guidance_scale=2.0)
+    out["pipe_df_latents_steps_9_10_11"] = lat.contiguous()
+    out["pipe_df_frame"] = pipe.frames[0].contiguous()
+    report["pipe_df_latents_steps_9_10_11"] = {
+        "shape": list(lat.shape), "absmax": lat.abs().max().item(),
+        "oracle_max_abs_diff": (lat - x).abs().max().item()}
+
+    batch = condition_batch()
+    for name, (over, kw) in CONDITION_CASES.items():
+        common = dict(CONDITION_COMMON, **over)
+        rc = ref_pipe.CrossviewTemporalSD.get_conditions(
+            ref, None, None, common, shape, batch, "cpu", torch.float32, **kw)
+        keys = []
+        for k, v in rc.items():
+            if v is not None:
+                out["cond_%s_%s" % (name, k)] = (v.to(torch.uint8) if v.dtype == torch.bool
+                                                 else v).contiguous()
+                keys.append(k)
+        report["cond_" + name] = {"keys": keys,
+                                  "none_keys": [k for k, v in rc.items() if v is None]}
 
     si = scheduler_inputs()
     fm = ref_sched.FlowMatchEulerDiscreteScheduler(num_train_timesteps=1000, shift=3.0)

@@ -11,7 +11,8 @@ import os
 import pytest
 import torch
 
-from common import VARIANTS, scheduler_inputs, seeded_oracle, variant_case
+from common import (CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS, condition_batch,
+                    scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SD21 = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
@@ -81,6 +82,52 @@ def test_oracle_schedulers_match_reference(golden):
                           golden["ddpm_get_velocity"], rtol=0, atol=1e-6)
 
 
+def test_oracle_df_loop_matches_reference_loop(golden):
+    """Three iterations (i = 9, 10, 11 of 12; CFG 2.0) of the reference's
+    StreamingCrossviewTemporalSD.inference_pipeline vs the oracle's df_denoise_step."""
+    from oracle import ctsd as octsd
+    torch.set_num_threads(1)
+    o = seeded_oracle(TINY)
+    sample, _, cond = synthetic_inputs(TINY)
+    sched = octsd.FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(12)
+    x = sample[:1].clone()
+    for i in (9, 10, 11):
+        x, _ = octsd.df_denoise_step(o, sched, x, cond, i=i, steps_per_inference=3,
+                                     guidance_scale=2.0)
+    ref = golden["pipe_df_latents_steps_9_10_11"]
+    assert (x - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    # the emitted frame = identity-VAE decode of the exiting latent frame, post-processed
+    frame = (ref[:, 0].flatten(0, 1) / 2 + 0.5).clamp(0, 1)
+    assert torch.allclose(frame, golden["pipe_df_frame"], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", list(CONDITION_CASES))
+def test_mirror_get_conditions_matches_reference(name, golden):
+    """The mirrored CrossviewTemporalSD.get_conditions / get_camera_transform_ids /
+    get_action_ids (pure PyTorch host code) against the reference's own, key by key."""
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    over, kw = CONDITION_CASES[name]
+    common = dict(CONDITION_COMMON, **over)
+    model = DiTCrossviewTemporalConditionModel(**TINY)       # isinstance checks only
+    batch = condition_batch()
+    got = CrossviewTemporalSD.get_conditions(
+        model, None, None, common, (1, 4, 3, 16, 8, 12), batch, "cpu", torch.float32, **kw)
+    prefix = "cond_%s_" % name
+    want = {k[len(prefix):]: v for k, v in golden.items() if k.startswith(prefix)}
+    assert want, name
+    for k, v in want.items():
+        g = got[k]
+        assert g is not None, k
+        g = g.to(torch.uint8) if g.dtype == torch.bool else g
+        assert g.shape == v.shape and g.dtype == v.dtype, (k, g.shape, v.shape, g.dtype)
+        assert torch.allclose(g.float(), v.float(), rtol=1e-5, atol=1e-5), k
+    for k, g in got.items():                                 # nothing extra is non-None
+        if g is not None and k != "pooled_projections":
+            assert k in want, k
+
+
 def test_df_index_schedule_matches_reference_loop_arithmetic():
     """The diffusion-forcing index expression of the reference loop (ctsd.py:2048-2055 and
     :2083-2088) evaluated literally, against the oracle and the mirrored helpers."""
@@ -111,6 +158,28 @@ def test_cuda_dit_matches_reference(name, golden):
     y = m(sample.cuda(), timestep.cuda(), **cond, **extra)
     y = y["noise_pred"] if extra else y[0][0]
     assert _rel(y.cpu(), golden["dit_" + name]) < 4e-3
+
+
+@pytest.mark.gpu
+def test_cuda_df_loop_matches_reference_loop(golden):
+    """The mirrored pipeline's denoise_step for i = 9, 10, 11 (fp16 compute) against the
+    latents the reference's own streaming loop produced."""
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import StreamingCrossviewTemporalSD
+    o = seeded_oracle(TINY)
+    m = DiTCrossviewTemporalConditionModel(**TINY, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    pipe = StreamingCrossviewTemporalSD(
+        None, {"generator_seed": 0}, "cuda", {"frame_prediction_style": "diffusion_forcing"},
+        {}, {"guidance_scale": 2.0, "inference_steps": 12, "sequence_length_per_iteration": 4},
+        None, m, model_dtype=torch.float32)
+    sample, _, cond = synthetic_inputs(TINY, device="cuda")
+    pipe.reset_streaming((1, 4, 3, 16, 8, 12), "pt")
+    lat = sample[:1].clone().float()
+    for i in (9, 10, 11):
+        idx, ts, in_range = pipe._df_step_tensors(i, 4, 3, 0, 1, 3)
+        pipe.denoise_step(lat, cond, idx, ts, in_range)
+    assert _rel(lat.cpu(), golden["pipe_df_latents_steps_9_10_11"]) < 4e-3
 
 
 @pytest.mark.gpu
