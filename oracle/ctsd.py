@@ -491,3 +491,106 @@ class DDIMSchedulerOracle:
             x0 = a_t ** 0.5 * sample - b_t ** 0.5 * model_output
             eps = a_t ** 0.5 * model_output + b_t ** 0.5 * sample
         return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
+
+
+class DPMSolverMultistepSchedulerOracle:
+    """diffusers==0.31.0 DPMSolverMultistepScheduler, the scheduler the reference's image
+    example selects (examples/ctsd_21_6views_image_generation.json `inference_config.scheduler`,
+    consumed at ctsd.py:981-985 and stepped with a scalar timestep at :1573-1575), restated for
+    algorithm_type "dpmsolver++", solver_type "midpoint", solver_order <= 2, no Karras sigmas,
+    no thresholding (the diffusers defaults on top of the SD-2.1 scheduler_config.json).
+    PARITY UNPINNED (restated from the published source)."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02,
+                 beta_schedule="linear", solver_order=2, prediction_type="epsilon",
+                 lower_order_final=True, euler_at_final=False, final_sigmas_type="zero",
+                 timestep_spacing="linspace", steps_offset=0, **unused):
+        import numpy as np
+        self.np = np
+        self.num_train_timesteps = num_train_timesteps
+        self.solver_order, self.prediction_type = solver_order, prediction_type
+        self.lower_order_final, self.euler_at_final = lower_order_final, euler_at_final
+        self.final_sigmas_type = final_sigmas_type
+        self.timestep_spacing, self.steps_offset = timestep_spacing, steps_offset
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps,
+                                   dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.init_noise_sigma = 1.0
+
+    def set_timesteps(self, n, device=None):
+        np = self.np
+        last = self.num_train_timesteps            # lambda_min_clipped = -inf: nothing clipped
+        if self.timestep_spacing == "linspace":
+            ts = np.linspace(0, last - 1, n + 1).round()[::-1][:-1].copy().astype(np.int64)
+        elif self.timestep_spacing == "leading":
+            ratio = last // (n + 1)
+            ts = (np.arange(0, n + 1) * ratio).round()[::-1][:-1].copy().astype(np.int64)
+            ts += self.steps_offset
+        elif self.timestep_spacing == "trailing":
+            ratio = self.num_train_timesteps / n
+            ts = np.arange(last, 0, -ratio).round().copy().astype(np.int64) - 1
+        else:
+            raise ValueError(self.timestep_spacing)
+        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = np.interp(ts, np.arange(0, len(sig)), sig)
+        if self.final_sigmas_type == "zero":
+            last_sigma = 0.0
+        else:
+            last_sigma = float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5)
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [last_sigma]]).astype(np.float32))
+        self.timesteps = torch.from_numpy(ts)
+        self.num_inference_steps = n
+        self.model_outputs = [None] * self.solver_order
+        self.lower_order_nums = 0
+        self.step_index = 0
+
+    @staticmethod
+    def _alpha_sigma(sigma):
+        alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
+        return alpha_t, sigma * alpha_t
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def step(self, model_output, timestep, sample):
+        i = self.step_index
+        n = len(self.timesteps)
+        lower_final = i == n - 1 and (self.euler_at_final or
+                                      (self.lower_order_final and n < 15) or
+                                      self.final_sigmas_type == "zero")
+        alpha_t, sigma_t = self._alpha_sigma(self.sigmas[i])
+        if self.prediction_type == "epsilon":
+            x0 = (sample - sigma_t * model_output) / alpha_t
+        elif self.prediction_type == "sample":
+            x0 = model_output
+        else:
+            x0 = alpha_t * sample - sigma_t * model_output
+        for k in range(self.solver_order - 1):
+            self.model_outputs[k] = self.model_outputs[k + 1]
+        self.model_outputs[-1] = x0
+        sample = sample.to(torch.float32)
+
+        def lam(sigma):
+            a, s = self._alpha_sigma(sigma)
+            return a, s, torch.log(a) - torch.log(s)
+        a_t, s_t, l_t = lam(self.sigmas[i + 1])
+        a_0, s_0, l_0 = lam(self.sigmas[i])
+        h = l_t - l_0
+        if self.solver_order == 1 or self.lower_order_nums < 1 or lower_final:
+            prev = (s_t / s_0) * sample - (a_t * (torch.exp(-h) - 1.0)) * x0
+        else:
+            a_1, s_1, l_1 = lam(self.sigmas[i - 1])
+            m0, m1 = self.model_outputs[-1], self.model_outputs[-2]
+            r0 = (l_0 - l_1) / h
+            d0, d1 = m0, (1.0 / r0) * (m0 - m1)
+            prev = (s_t / s_0) * sample - (a_t * (torch.exp(-h) - 1.0)) * d0 \
+                - 0.5 * (a_t * (torch.exp(-h) - 1.0)) * d1
+        if self.lower_order_nums < self.solver_order:
+            self.lower_order_nums += 1
+        self.step_index += 1
+        return prev.to(model_output.dtype)

@@ -266,6 +266,8 @@ class CrossviewTemporalSD:
         # the reference's defaults / examples name diffusers classes; map them to mirrors
         name = {"diffusers.DDIMScheduler":
                 "dwm.schedulers.temporal_independent.DDIMScheduler",
+                "diffusers.DPMSolverMultistepScheduler":
+                "dwm.schedulers.dpm_solver.DPMSolverMultistepScheduler",
                 "diffusers.FlowMatchEulerDiscreteScheduler": default_scheduler}.get(
                     name, name)
         test_scheduler_type = dwm.common.get_class(name)
@@ -377,7 +379,8 @@ class CrossviewTemporalSD:
         cudaGraphLaunch.  The first call per (latents, conditions) pair runs one eager
         warm-up step on a scratch copy (lazy weight packing, condition caches, workspace)
         and captures."""
-        if self.sharding is not None:
+        stateful = not self.is_dit and not hasattr(self.test_scheduler, "final_alpha_cumprod")
+        if self.sharding is not None or stateful:      # multistep schedulers keep host state
             return self.denoise_step(latents, conditions, idx, timesteps, in_range)
         key = (latents.data_ptr(), tuple(latents.shape), idx is None, in_range is None,
                tuple(sorted((k, v.data_ptr()) for k, v in conditions.items()
@@ -421,6 +424,21 @@ class CrossviewTemporalSD:
             crossview_attention_mask=conditions.get("crossview_attention_mask"),
             added_time_ids=conditions.get("added_time_ids"))
         sch = self.test_scheduler
+        if not hasattr(sch, "final_alpha_cumprod"):
+            # generic scheduler (e.g. DPM-Solver++ multistep, reference :1573-1575): CFG
+            # combine, then the scheduler's own scalar-timestep step (it counts steps itself)
+            pred = out[0].float().contiguous()
+            if do_cfg:
+                g = float(self.inference_config.get("guidance_scale", 1))
+                w = self.__dict__.get("_cfg_w")
+                if w is None or w[2] != g or w[0].device != pred.device:
+                    w = self._cfg_w = (torch.tensor([1.0 - g], device=pred.device),
+                                       torch.tensor([g], device=pred.device), g)
+                u, c = pred[:pred.shape[0] // 2], pred[pred.shape[0] // 2:]
+                pred = _ops.lincomb2(u.contiguous(), c.contiguous(), w[0], w[1],
+                                     torch.empty_like(u))          # u + g (c - u)
+            latents.copy_(sch.step(pred, timesteps.flatten()[0], latents).prev_sample)
+            return latents
         sch.alphas_cumprod = sch.alphas_cumprod.to(latents.device)
         _ops.cfg_ddim_step(
             out[0].float().contiguous(), latents,
@@ -493,6 +511,8 @@ class CrossviewTemporalSD:
         use_graph = self.inference_config.get(
             "cuda_graph", os.environ.get("DWM_CUDA_GRAPH", "0") == "1")
         step = self.denoise_step_graphed if use_graph else self.denoise_step
+        if hasattr(self.test_scheduler, "set_begin_index"):
+            self.test_scheduler.set_begin_index(start_timestep)
         for i in range(start_timestep, stop_timestep):
             if df_mode:
                 idx, timesteps, in_range = self._df_step_tensors(

@@ -190,3 +190,49 @@ def test_cuda_graph_step_matches_eager():
     assert torch.isfinite(a).all()
     noise = (a - a2).abs().max().item()
     assert (a - b).abs().max().item() <= max(4 * noise, 2e-2 * a.abs().max().item()), noise
+
+
+def test_unet_dpm_solver_pipeline_matches_oracle_loop():
+    """The image example's scheduler (`diffusers.DPMSolverMultistepScheduler`) through the
+    pipeline class: CFG + UNet + DPM-Solver++ 2M for 4 steps against an fp32 oracle loop."""
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel as U
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    from oracle.ctsd import DPMSolverMultistepSchedulerOracle
+    from test_unet import UCFG, _oracle
+    o = _oracle(UCFG).cuda()
+    m = U(**UCFG, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    common = dict(COMMON, frame_prediction_style="ctsd")
+    inf = {"guidance_scale": 3.0, "inference_steps": 4,
+           "scheduler": "diffusers.DPMSolverMultistepScheduler"}
+    pipe = CrossviewTemporalSD(None, {"generator_seed": 0}, "cuda", common, {}, inf, None, m,
+                               model_dtype=torch.float32)
+    assert type(pipe.test_scheduler).__name__ == "DPMSolverMultistepScheduler"
+    B, T, V = 1, 2, 3
+    shape = (B, T, V, 4, 16, 24)
+    batch = _batch(T, V, dict(joint_attention_dim=96, pooled_projection_dim=8), hw=(128, 192))
+    r = pipe.inference_pipeline(shape, batch, "pt")
+    sch = DPMSolverMultistepSchedulerOracle(
+        beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1,
+        prediction_type="v_prediction")
+    sch.set_timesteps(4)
+    assert pipe.test_scheduler.timesteps.tolist() == sch.timesteps.tolist()
+
+    lat = torch.randn(shape, generator=torch.Generator().manual_seed(0)).cuda()
+    cond = CrossviewTemporalSD.get_conditions(
+        m, object(), None, common, shape, batch, "cuda", torch.float32,
+        do_classifier_free_guidance=True)
+    with torch.no_grad():
+        for t in sch.timesteps.tolist():
+            tt = torch.full((2 * B, T, V), t, device="cuda")
+            out = o(torch.cat([lat, lat]), tt.float(),
+                    encoder_hidden_states=cond["encoder_hidden_states"],
+                    condition_image_tensor=cond["condition_image_tensor"],
+                    disable_crossview=cond["disable_crossview"],
+                    disable_temporal=cond["disable_temporal"],
+                    crossview_attention_mask=cond["crossview_attention_mask"],
+                    added_time_ids=cond["added_time_ids"])[0]
+            u, c = out.chunk(2)
+            lat = sch.step(u + 3.0 * (c - u), t, lat)
+    err = ((r["latents"] - lat).abs().max() / lat.abs().max()).item()
+    assert err < 1e-2, err

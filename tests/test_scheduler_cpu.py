@@ -3,6 +3,8 @@ committed golden tables; the oracle reproduces its own golden fixture."""
 import json
 import os
 
+import pytest
+
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -107,3 +109,41 @@ def test_oracle_known_answers():
     pe = d31.PatchEmbed(16, 16, 2, 4, 8, 6)
     full = pe.pos_embed.view(6, 6, 8)
     torch.testing.assert_close(pe.cropped_pos_embed(4, 8).view(2, 4, 8), full[2:4, 1:5])
+
+
+def test_dpm_solver_tables_and_coefficients_match_oracle():
+    """`diffusers.DPMSolverMultistepScheduler` mirror (the image example's scheduler): integer
+    timesteps and sigma tables equal the oracle restatement; the per-step coefficient table the
+    CUDA `step` consumes reproduces the oracle's trajectory when evaluated with plain torch."""
+    import torch
+    from dwm.schedulers.dpm_solver import DPMSolverMultistepScheduler as M
+    from oracle.ctsd import DPMSolverMultistepSchedulerOracle as O
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1)
+    m = M(prediction_type="v_prediction", **kw)
+    m.set_timesteps(50)
+    assert m.timesteps[:3].tolist() == [999, 979, 959] and m.timesteps[-1].item() == 20
+    assert m.sigmas[-1].item() == 0.0 and m.init_noise_sigma == 1.0
+    for pt in ("v_prediction", "epsilon", "sample"):
+        for spacing in ("linspace", "leading", "trailing"):
+            for n in (50, 10, 1):
+                m = M(prediction_type=pt, timestep_spacing=spacing, **kw)
+                o = O(prediction_type=pt, timestep_spacing=spacing, **kw)
+                m.set_timesteps(n)
+                o.set_timesteps(n)
+                assert m.timesteps.tolist() == o.timesteps.tolist()     # INT, bit exact
+                assert torch.equal(m.sigmas, o.sigmas)
+                g = torch.Generator().manual_seed(0)
+                x = torch.randn(2, 3, 4, generator=g)
+                xo, hist, lower = x.clone(), [None, None], 0
+                for i in range(n):
+                    v = torch.randn(2, 3, 4, generator=g) * 0.3
+                    first = lower < 1 or i == n - 1
+                    co = m._coef[i, 0 if first else 1]
+                    x0 = co[0] * x + co[1] * v
+                    hist = [hist[1], x0]
+                    x = co[2] * x + co[3] * x0 + (0 if first else co[4] * hist[0])
+                    lower = min(lower + 1, 2)
+                    xo = o.step(v, o.timesteps[i], xo)
+                assert ((x - xo).abs().max() / xo.abs().max()).item() < 2e-5, (pt, spacing, n)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.step(torch.zeros(2, 3, 4), None, torch.zeros(2, 3, 4))

@@ -41,3 +41,25 @@ def test_ddpm_add_noise_and_velocity():
     t = torch.randint(0, 1000, (2, 2, 3), generator=g).cuda()
     torch.testing.assert_close(s.add_noise(x, n, t), r.add_noise(x, n, t), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(s.get_velocity(x, n, t), r.get_velocity(x, n, t), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("ptype", ["v_prediction", "epsilon", "sample"])
+def test_dpm_solver_multistep(ptype):
+    """DPM-Solver++ (2M, midpoint) mirror: a whole 10-step trajectory on the GPU against the
+    oracle restatement of diffusers' DPMSolverMultistepScheduler."""
+    from dwm.schedulers.dpm_solver import DPMSolverMultistepScheduler
+    from oracle import ctsd as o
+    kw = dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", steps_offset=1,
+              prediction_type=ptype)
+    s, r = DPMSolverMultistepScheduler(**kw), o.DPMSolverMultistepSchedulerOracle(**kw)
+    s.set_timesteps(10, "cuda")
+    r.set_timesteps(10)
+    assert s.timesteps.cpu().tolist() == r.timesteps.tolist()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 2, 3, 4, 8, 6, generator=g)
+    xs, xr = x.cuda(), x.clone()
+    for i in range(10):
+        v = torch.randn(1, 2, 3, 4, 8, 6, generator=g) * 0.3
+        xs = s.step(v.cuda(), s.timesteps[i], xs).prev_sample
+        xr = r.step(v, r.timesteps[i], xr)
+        torch.testing.assert_close(xs.cpu(), xr, rtol=5e-5, atol=5e-5)
