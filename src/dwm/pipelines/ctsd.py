@@ -563,6 +563,105 @@ class CrossviewTemporalSD:
         return {"images": images, "latents": latents}
 
 
+    # -- long sequences: window after window ------------------------------------------------
+    def get_latent_sequence_length(self, sequence_length):
+        """Frames -> latent frames under a temporal VAE (`vae_pre` leading frames kept 1:1,
+        the rest compressed by `vae_stride`); identity for image VAEs (reference :1113-1118)."""
+        pre = self.inference_config.get("vae_pre", 0)
+        stride = self.inference_config.get("vae_stride", 1)
+        assert sequence_length % stride == pre or sequence_length == 0, \
+            "{} vs {} vs {}".format(sequence_length, pre, stride)
+        return (sequence_length - pre) // stride + (1 if pre > 0 else 0)
+
+    def _window(self, batch, start, stop):
+        keep = self.inference_config.get(
+            "autoregression_data_exception_for_take_sequence", [])
+        return {k: v if k in keep else dwm.functional.take_sequence_clip(v, start, stop)
+                for k, v in batch.items()}
+
+    @torch.no_grad()
+    def autoregressive_inference_pipeline(self, latent_shape, batch, output_type):
+        """Generates `batch["pts"].shape[1]` frames with windows of
+        `sequence_length_per_iteration` frames (reference :1656-1833).
+
+        Full-sequence style: every window re-uses the last `reference_frame_count` frames of
+        the previous one as clean reference latents and contributes the frames after them.
+        Diffusion-forcing style: the window is a queue of latents at staggered noise levels;
+        a warm-up pass fills it, then every iteration runs `steps_per_inference` steps, emits
+        the head frame, and (once `clear_reference_frame_count` heads are done) rotates the
+        queue with a fresh noise frame at the tail; the tail is flushed at the end."""
+        inf = self.inference_config
+        n_total = batch["pts"].shape[1]
+        win = inf["sequence_length_per_iteration"]
+        n_ref = inf.get("reference_frame_count", 1)
+        df_mode = self.common_config.get("frame_prediction_style") == "diffusion_forcing"
+        if not inf.get("generate_frames_for_reference", True):
+            raise NotImplementedError(
+                "reference frames from batch[\"vae_images\"] need the VAE encoder, which is "
+                "outside this implementation (SURVEY.md §8(f)3); leave "
+                "generate_frames_for_reference at its default")
+        image_latents = None
+        images = []
+        stride = win - n_ref
+        starts = range(0, n_total - win + 1, stride)
+
+        def has_next(i):
+            return i + stride < n_total - win + 1
+
+        if not df_mode:
+            for i in starts:
+                ref_now = 0 if image_latents is None else n_ref
+                out = self.inference_pipeline(
+                    latent_shape, self._window(batch, i, i + win), output_type, image_latents,
+                    reference_frame_count=self.get_latent_sequence_length(ref_now))
+                images.append(out["images"][latent_shape[0] * ref_now * latent_shape[2]:])
+                if has_next(i):
+                    image_latents = out["latents"][:, -self.get_latent_sequence_length(n_ref):]
+        else:
+            assert n_total > win
+            steps = inf["inference_steps"]
+            clear = inf.get("clear_reference_frame_count", 0)
+            spi = steps // (latent_shape[1] - clear)
+            T = latent_shape[1]
+
+            def finished(head):      # queue slots whose frames are already final
+                return torch.tensor([j <= head for j in range(T)], device=self.device)\
+                    .view(1, T, 1, 1, 1, 1)
+            # warm-up: bring the queue to the staggered steady state
+            window = self._window(batch, 0, win)
+            image_latents = self.inference_pipeline(
+                latent_shape, window, output_type, None, reference_frame_count=0,
+                start_timestep=0, stop_timestep=steps - spi)["latents"]
+            head = -1
+            for i in starts:
+                window = self._window(batch, i, i + win)
+                ref_now = n_ref
+                if head < clear:
+                    ref_now = T
+                    head += 1
+                out = self.inference_pipeline(
+                    latent_shape, window, output_type, image_latents,
+                    reference_frame_count=ref_now,
+                    start_timestep=steps + (head - 1) * spi,
+                    stop_timestep=steps + head * spi, take_time=head)
+                images.append(out["images"].chunk(4)[-1]
+                              if self.is_temporal_vae and i == 0 else out["images"])
+                image_latents = torch.where(finished(head), image_latents, out["latents"])
+                if head == clear and has_next(i):
+                    fresh = torch.randn((latent_shape[0], 1) + tuple(latent_shape[2:]),
+                                        generator=self.generator).to(self.device) * \
+                        getattr(self.test_scheduler, "init_noise_sigma", 1)
+                    image_latents = torch.cat([image_latents[:, 1:], fresh], 1)
+            for j in range(head + 1, T):       # flush: the last window keeps its conditions
+                out = self.inference_pipeline(
+                    latent_shape, window, output_type, image_latents, reference_frame_count=T,
+                    start_timestep=steps + (j - 1) * spi, stop_timestep=steps + j * spi,
+                    take_time=j)
+                images.append(out["images"])
+                image_latents = torch.where(finished(j), image_latents, out["latents"])
+        return {"images": torch.cat(images) if output_type == "pt" else images}
+
+
 class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
 
     def reset_streaming(self, latent_shape, output_type):

@@ -177,3 +177,79 @@ CONDITION_CASES = {
                                     _3dbox_condition_mask=torch.tensor([[[True, False, True]]]),
                                     hdmap_condition_mask=torch.tensor([[[False, True, True]]]))),
 }
+
+
+# -- orchestration traces of autoregressive_inference_pipeline ---------------------------------
+
+AUTOREGRESSIVE_CASES = {
+    # name -> (common_config, inference_config, latent_shape, total frames, temporal VAE?)
+    "windows_ref2": ({"frame_prediction_style": "ctsd"},
+                     {"inference_steps": 8, "sequence_length_per_iteration": 6,
+                      "reference_frame_count": 2}, (1, 6, 3, 4, 2, 3), 14, False),
+    "temporal_vae_ref1": ({"frame_prediction_style": "ctsd"},
+                          {"inference_steps": 8, "sequence_length_per_iteration": 17,
+                           "reference_frame_count": 1, "vae_pre": 1, "vae_stride": 4,
+                           "generate_frames_for_reference": True},
+                          (1, 5, 3, 4, 2, 3), 33, True),
+    "diffusion_forcing": ({"frame_prediction_style": "diffusion_forcing"},
+                          {"inference_steps": 12, "sequence_length_per_iteration": 4,
+                           "autoregression_data_exception_for_take_sequence":
+                               ["crossview_mask"]},
+                          (1, 4, 3, 4, 2, 3), 9, False),
+    "diffusion_forcing_clear1": ({"frame_prediction_style": "diffusion_forcing"},
+                                 {"inference_steps": 12, "sequence_length_per_iteration": 4,
+                                  "clear_reference_frame_count": 1,
+                                  "reference_frame_count": 1},
+                                 (1, 4, 3, 4, 2, 3), 10, True),
+}
+
+
+def autoregressive_batch(n_frames, V=3):
+    return {"pts": torch.arange(n_frames).float().view(1, n_frames, 1).repeat(1, 1, V),
+            "fps": torch.tensor([10.0]),
+            "crossview_mask": torch.ones(1, V, V, dtype=torch.bool),
+            "clip_text": [["frame %d" % t for t in range(n_frames)]]}
+
+
+def install_fake_inference_pipeline(pipe, trace):
+    """Replaces `pipe.inference_pipeline` by a deterministic stand-in that records how the
+    orchestration calls it (the same stand-in drives the reference and the mirror)."""
+    def fake(latent_shape, batch, output_type, image_latents=None, reference_frame_count=0,
+             start_timestep=0, stop_timestep=None, take_time=0):
+        k = len(trace)
+        g = torch.Generator().manual_seed(1000 + k)
+        lat = torch.randn(tuple(latent_shape), generator=g)
+        B, T, V = latent_shape[:3]
+        n_img = B * (1 if stop_timestep is not None else T) * V
+        if pipe.is_temporal_vae and stop_timestep is None:
+            n_img = B * ((T - 1) * 4 + 1) * V
+        img = torch.arange(n_img).float().view(n_img, 1) + 1000 * k
+        trace.append({
+            "latent_shape": list(latent_shape), "pts": batch["pts"][0, :, 0].tolist(),
+            "clip_text": batch["clip_text"][0], "mask_shape": list(batch["crossview_mask"].shape),
+            "output_type": output_type,
+            "image_latents": None if image_latents is None else
+            [list(image_latents.shape), round(float(image_latents.double().sum()), 4)],
+            "reference_frame_count": int(reference_frame_count),
+            "start_timestep": int(start_timestep),
+            "stop_timestep": None if stop_timestep is None else int(stop_timestep),
+            "take_time": int(take_time)})
+        return {"images": img, "latents": lat}
+    pipe.inference_pipeline = fake
+
+
+def run_autoregressive_case(cls, name):
+    """Drives `cls.autoregressive_inference_pipeline` (reference or mirror class) without
+    building a pipeline: only the attributes the orchestration reads are set."""
+    common, inf, shape, n_frames, temporal = AUTOREGRESSIVE_CASES[name]
+    pipe = object.__new__(cls)
+    pipe.common_config, pipe.inference_config, pipe.training_config = common, inf, {}
+    pipe.device = torch.device("cpu")
+    pipe.generator = torch.Generator().manual_seed(0)
+    pipe.is_temporal_vae = temporal
+    pipe.test_scheduler = type("S", (), {"init_noise_sigma": 1.0})()
+    trace = []
+    install_fake_inference_pipeline(pipe, trace)
+    out = pipe.autoregressive_inference_pipeline(shape, autoregressive_batch(n_frames), "pt")
+    return {"calls": trace, "images_shape": list(out["images"].shape),
+            "images_sum": float(out["images"].double().sum())}

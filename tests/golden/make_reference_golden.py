@@ -15,7 +15,9 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
   dwm/pipelines/ctsd.py                  StreamingCrossviewTemporalSD.reset_streaming +
                                          inference_pipeline (the diffusion-forcing loop, 3
                                          steps, CFG) and CrossviewTemporalSD.get_conditions /
-                                         get_camera_transform_ids / get_action_ids
+                                         get_camera_transform_ids / get_action_ids;
+                                         autoregressive_inference_pipeline (call traces with a
+                                         stand-in inference_pipeline, four configurations)
   dwm/schedulers/temporal_independent.py FlowMatchEulerDiscreteScheduler.step_by_indices,
                                          DDIMScheduler.step, DDPMScheduler.add_noise /
                                          get_velocity (tensor timesteps)
@@ -37,7 +39,8 @@ sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(RO
 
 import torch  # noqa: E402
 
-from common import (CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS,  # noqa: E402
+from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON,  # noqa: E402
+                    TINY, VARIANTS, run_autoregressive_case,
                     condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
@@ -162,7 +165,14 @@ def main():
     out["ddpm_get_velocity"] = ddpm.get_velocity(
         si["sample"], si["noise"], si["ddpm_timesteps"]).contiguous()
 
+    # ---- orchestration of autoregressive_inference_pipeline (ctsd.py:1656-1833): how the
+    #      reference drives inference_pipeline window after window, recorded with a stand-in ----
+    traces = {name: run_autoregressive_case(ref_pipe.CrossviewTemporalSD, name)
+              for name in AUTOREGRESSIVE_CASES}
+
     safetensors.torch.save_file(out, os.path.join(HERE, "reference_outputs.safetensors"))
+    with open(os.path.join(HERE, "reference_autoregressive_traces.json"), "w") as f:
+        json.dump(traces, f, indent=1)
     with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
         json.dump({"generated_from": "/root/reference/src (OpenDWM @ b0ecc3d) on the "
                                      "diffusers shim tests/golden/diffusers_stub",

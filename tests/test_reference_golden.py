@@ -11,7 +11,8 @@ import os
 import pytest
 import torch
 
-from common import (CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS, condition_batch,
+from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS,
+                    condition_batch, run_autoregressive_case,
                     scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -126,6 +127,24 @@ def test_mirror_get_conditions_matches_reference(name, golden):
     for k, g in got.items():                                 # nothing extra is non-None
         if g is not None and k != "pooled_projections":
             assert k in want, k
+
+
+@pytest.mark.parametrize("name", list(AUTOREGRESSIVE_CASES))
+def test_mirror_autoregressive_orchestration_matches_reference(name):
+    """Window / queue orchestration of long sequences (full-sequence with reference frames,
+    temporal-VAE frame arithmetic, diffusion-forcing warm-up / rotate / flush): the mirror
+    must call inference_pipeline exactly like the reference does — same windows, reference
+    frame counts, step ranges, take_time, and the same latent state handed from call to call."""
+    import json
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    with open(os.path.join(HERE, "golden", "reference_autoregressive_traces.json")) as f:
+        want = json.load(f)[name]
+    got = json.loads(json.dumps(run_autoregressive_case(CrossviewTemporalSD, name)))
+    assert len(got["calls"]) == len(want["calls"])
+    for a, b in zip(got["calls"], want["calls"]):
+        assert a == b
+    assert got["images_shape"] == want["images_shape"]
+    assert got["images_sum"] == want["images_sum"]
 
 
 def test_df_index_schedule_matches_reference_loop_arithmetic():
