@@ -253,3 +253,46 @@ def run_autoregressive_case(cls, name):
     out = pipe.autoregressive_inference_pipeline(shape, autoregressive_batch(n_frames), "pt")
     return {"calls": trace, "images_shape": list(out["images"].shape),
             "images_sum": float(out["images"].double().sum())}
+
+
+# -- orchestration trace of the streaming FIFO (send_frame_condition / receive_frame /
+#    fifo_inference_pipeline) ---------------------------------------------------------------------
+
+def run_fifo_case(cls, model, n_frames=7):
+    """Drives `cls.fifo_inference_pipeline` (reference or mirror StreamingCrossviewTemporalSD)
+    with the real get_conditions (text-less) and a recording stand-in for the denoising loop."""
+    pipe = object.__new__(cls)
+    pipe.common_config = dict(CONDITION_COMMON, added_time_ids="fps_camera_transforms_action",
+                              camera_ego_sensor_indices=[1, 2, 3])
+    pipe.inference_config = {
+        "guidance_scale": 2.0, "inference_steps": 12, "sequence_length_per_iteration": 4,
+        "text_prompt_interval": 1,
+        "autoregression_data_exception_for_take_sequence": ["crossview_mask"],
+        "autoregression_condition_exception_for_take_sequence": [
+            "disable_crossview", "disable_temporal", "crossview_attention_mask",
+            "camera_intrinsics_norm", "camera2referego", "encoder_hidden_states"]}
+    pipe.device, pipe.model_dtype = torch.device("cpu"), torch.float32
+    pipe.generator = torch.Generator().manual_seed(0)
+    pipe.model = pipe.model_wrapper = model
+    pipe.text_encoders = pipe.tokenizers = pipe.tokenizer = None
+    pipe.test_scheduler = type("S", (), {"init_noise_sigma": 1.0,
+                                         "set_timesteps": lambda self, n, device=None: None})()
+    trace = []
+
+    def summary(d):
+        return {k: [list(v.shape), round(float(v.double().sum()), 3)]
+                for k, v in sorted(d.items()) if v is not None}
+
+    def fake(latent_shape, start_timestep=0, stop_timestep=None, take_time=0):
+        k = len(trace)
+        lat = torch.randn(tuple(latent_shape), generator=torch.Generator().manual_seed(500 + k))
+        trace.append({"start": int(start_timestep), "stop": int(stop_timestep),
+                      "take_time": int(take_time), "conditions": summary(pipe.conditions),
+                      "latents_in": round(float(pipe.latents.double().sum()), 3)})
+        if stop_timestep >= pipe.inference_config["inference_steps"]:
+            pipe.frames.append(lat[:, take_time].flatten(0, 1))
+        return lat
+    pipe.inference_pipeline = fake
+    out = pipe.fifo_inference_pipeline((1, 4, 3, 4, 2, 3), condition_batch(T=n_frames), "pt")
+    return {"calls": trace, "images_shape": list(out["images"].shape),
+            "images_sum": round(float(out["images"].double().sum()), 3)}

@@ -17,7 +17,10 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
                                          steps, CFG) and CrossviewTemporalSD.get_conditions /
                                          get_camera_transform_ids / get_action_ids;
                                          autoregressive_inference_pipeline (call traces with a
-                                         stand-in inference_pipeline, four configurations)
+                                         stand-in inference_pipeline, four configurations);
+                                         StreamingCrossviewTemporalSD.fifo_inference_pipeline /
+                                         send_frame_condition / receive_frame (call + state
+                                         trace over 7 frames)
   dwm/schedulers/temporal_independent.py FlowMatchEulerDiscreteScheduler.step_by_indices,
                                          DDIMScheduler.step, DDPMScheduler.add_noise /
                                          get_velocity (tensor timesteps)
@@ -40,7 +43,7 @@ sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(RO
 import torch  # noqa: E402
 
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON,  # noqa: E402
-                    TINY, VARIANTS, run_autoregressive_case,
+                    TINY, VARIANTS, run_autoregressive_case, run_fifo_case,
                     condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
@@ -169,6 +172,10 @@ def main():
     #      reference drives inference_pipeline window after window, recorded with a stand-in ----
     traces = {name: run_autoregressive_case(ref_pipe.CrossviewTemporalSD, name)
               for name in AUTOREGRESSIVE_CASES}
+    # streaming FIFO (ctsd.py:2012-2278): reset_streaming / send_frame_condition /
+    # receive_frame / fifo_inference_pipeline with the real streaming-mode get_conditions
+    traces["streaming_fifo"] = run_fifo_case(
+        ref_pipe.StreamingCrossviewTemporalSD, object.__new__(diffusers.SD3Transformer2DModel))
 
     safetensors.torch.save_file(out, os.path.join(HERE, "reference_outputs.safetensors"))
     with open(os.path.join(HERE, "reference_autoregressive_traces.json"), "w") as f:

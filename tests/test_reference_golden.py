@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS,
-                    condition_batch, run_autoregressive_case,
+                    condition_batch, run_autoregressive_case, run_fifo_case,
                     scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -145,6 +145,24 @@ def test_mirror_autoregressive_orchestration_matches_reference(name):
         assert a == b
     assert got["images_shape"] == want["images_shape"]
     assert got["images_sum"] == want["images_sum"]
+
+
+def test_mirror_streaming_fifo_matches_reference():
+    """FIFO streaming (condition queue, latent queue rotation with fresh noise, streaming-mode
+    get_conditions with the previous ego pose, flush): per denoising call the step range,
+    take_time, every condition tensor's shape + checksum and the latent state must equal the
+    reference's, and so must the emitted frames."""
+    import json
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import StreamingCrossviewTemporalSD
+    with open(os.path.join(HERE, "golden", "reference_autoregressive_traces.json")) as f:
+        want = json.load(f)["streaming_fifo"]
+    got = json.loads(json.dumps(run_fifo_case(
+        StreamingCrossviewTemporalSD, object.__new__(DiTCrossviewTemporalConditionModel))))
+    assert len(got["calls"]) == len(want["calls"]) == 7
+    for a, b in zip(got["calls"], want["calls"]):
+        assert a == b
+    assert got["images_shape"] == want["images_shape"] and got["images_sum"] == want["images_sum"]
 
 
 def test_df_index_schedule_matches_reference_loop_arithmetic():
