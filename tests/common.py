@@ -296,3 +296,23 @@ def run_fifo_case(cls, model, n_frames=7):
     out = pipe.fifo_inference_pipeline((1, 4, 3, 4, 2, 3), condition_batch(T=n_frames), "pt")
     return {"calls": trace, "images_shape": list(out["images"].shape),
             "images_sum": round(float(out["images"].double().sum()), 3)}
+
+
+# -- the full-sequence inference_pipeline (reference ctsd.py:1439-1654) ---------------------------
+
+FULL_SEQUENCE_CASES = {
+    # name -> (inference_config, reference_frame_count)
+    "plain": ({"guidance_scale": 3.0, "inference_steps": 3}, 0),
+    "reference_frames": ({"guidance_scale": 3.0, "inference_steps": 3}, 1),
+    "no_cfg_partial": ({"inference_steps": 4}, 0),
+}
+
+
+def full_sequence_inputs():
+    cfg = dict(TINY, projection_class_embeddings_input_dim=11 * 256)
+    batch = condition_batch(T=3, V=3, hw=(64, 96), text_dim=cfg["joint_attention_dim"],
+                            pooled_dim=cfg["pooled_projection_dim"])
+    common = dict(CONDITION_COMMON, frame_prediction_style="ctsd")
+    shape = (1, 3, 3, 16, 8, 12)
+    image_latents = torch.randn(shape, generator=torch.Generator().manual_seed(21))
+    return cfg, batch, common, shape, image_latents

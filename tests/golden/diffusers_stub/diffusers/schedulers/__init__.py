@@ -65,3 +65,21 @@ class FlowMatchEulerDiscreteScheduler(_d31.FlowMatchEulerDiscreteSchedulerBase):
     def __init__(self, num_train_timesteps=1000, shift=1.0, **unused):
         super().__init__(num_train_timesteps, shift)
         self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, shift=shift)
+        self._step_index = None
+
+    def set_timesteps(self, num_inference_steps, device=None):
+        super().set_timesteps(num_inference_steps, device)
+        self._step_index = None
+
+    def step(self, model_output, timestep, sample, return_dict=True, **unused):
+        """diffusers 0.31 scalar-timestep Euler step (used by the reference's full-sequence
+        loop, ctsd.py:1573-1575): the step index is found from the first timestep, then
+        counted."""
+        if self._step_index is None:
+            self._step_index = int((self.timesteps == timestep).nonzero()[0].item())
+        sample = sample.to(torch.float32)
+        sigma, sigma_next = self.sigmas[self._step_index], self.sigmas[self._step_index + 1]
+        prev = (sample + (sigma_next - sigma) * model_output).to(model_output.dtype)
+        self._step_index += 1
+        out = scheduling_flow_match_euler_discrete.FlowMatchEulerDiscreteSchedulerOutput(prev)
+        return out if return_dict else (prev,)

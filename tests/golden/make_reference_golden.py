@@ -12,7 +12,9 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
   dwm/models/crossview_temporal_unet.py  UNetCrossviewTemporalConditionModel + its five block
                                          classes; crossview_temporal.py ResBlock,
                                          TransformerModel, TemporalBasicTransformerBlock
-  dwm/pipelines/ctsd.py                  StreamingCrossviewTemporalSD.reset_streaming +
+  dwm/pipelines/ctsd.py                  CrossviewTemporalSD.inference_pipeline (full-sequence
+                                         loop, reference-frame injection, 3 configurations);
+                                         StreamingCrossviewTemporalSD.reset_streaming +
                                          inference_pipeline (the diffusion-forcing loop, 3
                                          steps, CFG) and CrossviewTemporalSD.get_conditions /
                                          get_camera_transform_ids / get_action_ids;
@@ -43,7 +45,8 @@ sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(RO
 import torch  # noqa: E402
 
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON,  # noqa: E402
-                    TINY, VARIANTS, run_autoregressive_case, run_fifo_case,
+                    FULL_SEQUENCE_CASES, TINY, VARIANTS, full_sequence_inputs,
+                    run_autoregressive_case, run_fifo_case,
                     condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
@@ -131,6 +134,53 @@ def main():
     report["pipe_df_latents_steps_9_10_11"] = {
         "shape": list(lat.shape), "absmax": lat.abs().max().item(),
         "oracle_max_abs_diff": (lat - x).abs().max().item()}
+
+    # ---- the reference's full-sequence inference_pipeline (ctsd.py:1439-1654): noise from the
+    #      pipeline generator, get_conditions, scalar-timestep FlowMatch steps, reference-frame
+    #      injection, final concatenation, VAE call site (identity VAE), post-processing.  Text
+    #      comes pre-encoded: get_conditions is wrapped to add the batch's embeddings (uncond =
+    #      zeros), everything else is the reference's ----------------------------------------------
+    fcfg, fbatch, fcommon, fshape, f_image_latents = full_sequence_inputs()
+    f_oracle = seeded_oracle(fcfg)
+    f_ref = ref_dit.DiTCrossviewTemporalConditionModel(**fcfg)
+    f_ref.load_state_dict(f_oracle.state_dict(), strict=True)
+    f_ref.eval()
+    f_ref.depth_net = None
+    P = ref_pipe.CrossviewTemporalSD
+    orig_gc = P.get_conditions
+
+    def gc_with_text(model, te, tok, common_config, latent_shape, b, device, dtype, **kw):
+        rc = orig_gc(model, None, None, common_config, latent_shape, b, device, dtype, **kw)
+        t_, p_ = b["text_embeddings"].to(dtype), b["pooled_text_embeddings"].to(dtype)
+        if kw.get("do_classifier_free_guidance"):
+            t_ = torch.cat([torch.zeros_like(t_), t_])
+            p_ = torch.cat([torch.zeros_like(p_), p_])
+        rc["encoder_hidden_states"], rc["pooled_projections"] = t_, p_
+        return rc
+    for name, (inf, nref) in FULL_SEQUENCE_CASES.items():
+        fp = object.__new__(P)
+        fp.common_config, fp.inference_config = fcommon, inf
+        fp.device, fp.model_dtype = torch.device("cpu"), torch.float32
+        fp.model = fp.model_wrapper = f_ref
+        fp.text_encoders = fp.tokenizers = None
+        fp.generator = torch.Generator().manual_seed(0)
+        fp.test_scheduler = ref_sched.FlowMatchEulerDiscreteScheduler(
+            num_train_timesteps=1000, shift=3.0)
+        fp.vae, fp.is_temporal_vae = IdentityVae(), False
+        fp.image_processor = diffusers.image_processor.VaeImageProcessor()
+        kw = dict(image_latents=f_image_latents, reference_frame_count=nref) if nref else {}
+        if name == "no_cfg_partial":
+            kw.update(start_timestep=1, stop_timestep=3)
+        P.get_conditions = staticmethod(gc_with_text)
+        try:
+            with torch.no_grad():
+                fo = fp.inference_pipeline(fshape, fbatch, "pt", **kw)
+        finally:
+            P.get_conditions = staticmethod(orig_gc)
+        out["fullseq_%s_latents" % name] = fo["latents"].contiguous()
+        out["fullseq_%s_images" % name] = fo["images"].contiguous()
+        report["fullseq_" + name] = {"shape": list(fo["latents"].shape),
+                                     "absmax": fo["latents"].abs().max().item()}
 
     batch = condition_batch()
     for name, (over, kw) in CONDITION_CASES.items():

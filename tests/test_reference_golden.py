@@ -11,7 +11,8 @@ import os
 import pytest
 import torch
 
-from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, TINY, VARIANTS,
+from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, FULL_SEQUENCE_CASES,
+                    TINY, VARIANTS, full_sequence_inputs,
                     condition_batch, run_autoregressive_case, run_fifo_case,
                     scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
@@ -129,6 +130,48 @@ def test_mirror_get_conditions_matches_reference(name, golden):
             assert k in want, k
 
 
+@pytest.mark.parametrize("name", list(FULL_SEQUENCE_CASES))
+def test_full_sequence_algorithm_matches_reference(name, golden):
+    """The mirror's full-sequence step algorithm — reference frames written into the latents
+    at timestep 0 before each step, Euler update of every frame, reference frames restored at
+    the end — evaluated with the fp32 oracle model, the mirror's get_conditions and scheduler
+    tables on the CPU, against the latents / images the reference's own inference_pipeline
+    produced (which instead swaps the reference frames into the model input only)."""
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    from oracle import ctsd as octsd
+    torch.set_num_threads(1)
+    inf, nref = FULL_SEQUENCE_CASES[name]
+    cfg, batch, common, shape, image_latents = full_sequence_inputs()
+    o = seeded_oracle(cfg)
+    do_cfg = "guidance_scale" in inf
+    cond = CrossviewTemporalSD.get_conditions(
+        object.__new__(DiTCrossviewTemporalConditionModel), object(), None, common, shape,
+        batch, "cpu", torch.float32, do_classifier_free_guidance=do_cfg)
+    sched = octsd.FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(inf["inference_steps"])
+    lat = torch.randn(shape, generator=torch.Generator().manual_seed(0))
+    start, stop = (1, 3) if name == "no_cfg_partial" else (0, inf["inference_steps"])
+    with torch.no_grad():
+        for i in range(start, stop):
+            ts = sched.timesteps[i].expand(shape[:3]).clone()
+            if nref:
+                lat[:, :nref] = image_latents[:, :nref]
+                ts[:, :nref] = 0
+            x, t = (torch.cat([lat, lat]), torch.cat([ts, ts])) if do_cfg else (lat, ts)
+            pred = o(x, t, **cond)[0][0]
+            if do_cfg:
+                u, c = pred.chunk(2)
+                pred = u + inf["guidance_scale"] * (c - u)
+            lat = lat + (sched.sigmas[i + 1] - sched.sigmas[i]) * pred
+    if nref:
+        lat = torch.cat([image_latents[:, :nref], lat[:, nref:]], 1)
+    ref = golden["fullseq_%s_latents" % name]
+    assert (lat - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    img = (lat.flatten(0, 2) / 2 + 0.5).clamp(0, 1)
+    assert torch.allclose(img, golden["fullseq_%s_images" % name], atol=1e-5)
+
+
 @pytest.mark.parametrize("name", list(AUTOREGRESSIVE_CASES))
 def test_mirror_autoregressive_orchestration_matches_reference(name):
     """Window / queue orchestration of long sequences (full-sequence with reference frames,
@@ -217,6 +260,28 @@ def test_cuda_df_loop_matches_reference_loop(golden):
         idx, ts, in_range = pipe._df_step_tensors(i, 4, 3, 0, 1, 3)
         pipe.denoise_step(lat, cond, idx, ts, in_range)
     assert _rel(lat.cpu(), golden["pipe_df_latents_steps_9_10_11"]) < 4e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(FULL_SEQUENCE_CASES))
+def test_cuda_full_sequence_pipeline_matches_reference(name, golden):
+    """CrossviewTemporalSD.inference_pipeline of the mirror (fp16 compute) against the
+    reference's own inference_pipeline outputs: same generator noise, conditions, reference
+    frame handling, step range."""
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    inf, nref = FULL_SEQUENCE_CASES[name]
+    cfg, batch, common, shape, image_latents = full_sequence_inputs()
+    m = DiTCrossviewTemporalConditionModel(**cfg, compute_dtype=torch.float16)
+    m.load_state_dict(seeded_oracle(cfg).state_dict())
+    pipe = CrossviewTemporalSD(None, {"generator_seed": 0}, "cuda", common, {}, dict(inf), None,
+                               m, model_dtype=torch.float32)
+    kw = dict(image_latents=image_latents.cuda(), reference_frame_count=nref) if nref else {}
+    if name == "no_cfg_partial":
+        kw.update(start_timestep=1, stop_timestep=3)
+    r = pipe.inference_pipeline(shape, batch, "pt", **kw)
+    assert _rel(r["latents"].cpu(), golden["fullseq_%s_latents" % name]) < 8e-3
+    assert r["images"].shape == golden["fullseq_%s_images" % name].shape
 
 
 @pytest.mark.gpu
