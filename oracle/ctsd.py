@@ -536,7 +536,7 @@ class DPMSolverMultistepSchedulerOracle:
             ts = np.arange(last, 0, -ratio).round().copy().astype(np.int64) - 1
         else:
             raise ValueError(self.timestep_spacing)
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         if self.final_sigmas_type == "zero":
             last_sigma = 0.0

@@ -110,7 +110,7 @@ class DPMSolverMultistepScheduler:
             ts = np.arange(last, 0, -ratio).round().copy().astype(np.int64) - 1
         else:
             raise ValueError(c.timestep_spacing)
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         last_sigma = 0.0 if c.final_sigmas_type == "zero" else \
             float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5)
