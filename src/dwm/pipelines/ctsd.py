@@ -123,6 +123,18 @@ class CrossviewTemporalSD:
                                 torch.zeros_like(pe)).to(device=device, dtype=dtype)
                 te, pe = torch.cat([ute, te]), torch.cat([upe, pe])
             encoder_hidden_states, pooled = te, pe
+        elif text_encoder is not None and "clip_text" in batch:
+            # reference-style prompts through the real text encoders (reference :176-253)
+            if isinstance(text_encoder, str):
+                raise RuntimeError(
+                    "the batch carries prompts (clip_text) but no text encoders were loaded: "
+                    "point pretrained_model_name_or_path at a checkpoint directory with "
+                    "tokenizer*/text_encoder* or pass pre-encoded text_embeddings")
+            from dwm.pipelines.text_conditions import text_conditions
+            encoder_hidden_states, pooled = text_conditions(
+                isinstance(model, _compat.SD3Transformer2DModelMarker), text_encoder, tokenizer,
+                batch["clip_text"], sequence_length, view_count, device, dtype,
+                text_condition_mask, do_classifier_free_guidance)
 
         condition_on_all_frames = common_config.get(
             "condition_on_all_frames", False)
@@ -235,6 +247,7 @@ class CrossviewTemporalSD:
         # text encoders are not part of this implementation: a truthy marker keeps
         # get_conditions on the "text provided" path when the batch is pre-encoded
         self.text_encoders = self.tokenizers = "pre-encoded"
+        self._text_pending = pretrained_model_name_or_path
         self.vae = common_config.get("vae_instance")
         self.is_temporal_vae = bool(common_config.get("vae_is_temporal", False))
         # reference :953-958: class named by common_config["vae"] (default
@@ -256,6 +269,13 @@ class CrossviewTemporalSD:
             self.is_temporal_vae = True
 
         self.is_dit = isinstance(self.model, _compat.SD3Transformer2DModelMarker)
+        if self._text_pending is not None:       # real encoders when the checkpoint has them
+            from dwm.pipelines.text_conditions import load_text_encoders
+            loaded = load_text_encoders(
+                self.is_dit, self._text_pending, self.device,
+                common_config.get("text_encoder_load_args", {}))
+            if loaded is not None:
+                self.text_encoders, self.tokenizers = loaded
         if not self.is_dit and not isinstance(
                 self.model, _compat.UNetSpatioTemporalConditionModelMarker):
             raise Exception("Unsupported diffusion model type.")

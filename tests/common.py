@@ -316,3 +316,95 @@ def full_sequence_inputs():
     shape = (1, 3, 3, 16, 8, 12)
     image_latents = torch.randn(shape, generator=torch.Generator().manual_seed(21))
     return cfg, batch, common, shape, image_latents
+
+
+# -- text conditions through (tiny, randomly initialised) Hugging Face encoders -------------------
+
+def tiny_text_stack():
+    """Byte-level CLIP tokenizer built in memory plus seeded tiny CLIP-L / CLIP-G / T5 stand-ins
+    and a CLIPTextModel (SD-2.1 path).  No files, no downloads."""
+    import transformers
+
+    def bytes_to_unicode():
+        bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAD)) + \
+            list(range(0xAE, 0x100))
+        cs, n = bs[:], 0
+        for b in range(256):
+            if b not in bs:
+                bs.append(b)
+                cs.append(256 + n)
+                n += 1
+        return [chr(c) for c in cs]
+    chars = sorted(set(bytes_to_unicode()))
+    vocab = {}
+    for c in chars:
+        vocab[c] = len(vocab)
+    for c in chars:
+        vocab[c + "</w>"] = len(vocab)
+    merges = [("t", "h"), ("th", "e</w>"), ("c", "a"), ("ca", "r</w>")]
+    for a, b in merges:
+        vocab[a + b] = len(vocab)
+    vocab["<|startoftext|>"], vocab["<|endoftext|>"] = len(vocab), len(vocab) + 1
+    tok = transformers.CLIPTokenizer(vocab=vocab, merges=merges)
+    tok.model_max_length = 77
+
+    def clip_cfg(hidden, proj):
+        return transformers.CLIPTextConfig(
+            vocab_size=len(vocab), hidden_size=hidden, intermediate_size=2 * hidden,
+            projection_dim=proj, num_hidden_layers=2, num_attention_heads=2,
+            max_position_embeddings=77, bos_token_id=vocab["<|startoftext|>"],
+            eos_token_id=vocab["<|endoftext|>"], pad_token_id=vocab["<|endoftext|>"])
+    torch.manual_seed(1234)
+    clip_l = transformers.CLIPTextModelWithProjection(clip_cfg(32, 24)).eval()
+    clip_g = transformers.CLIPTextModelWithProjection(clip_cfg(40, 16)).eval()
+    t5 = transformers.T5EncoderModel(transformers.T5Config(
+        vocab_size=len(vocab) + 2, d_model=96, d_kv=8, d_ff=64, num_layers=2,
+        num_heads=2)).eval()
+    clip_sd21 = transformers.CLIPTextModel(clip_cfg(48, 48)).eval()
+    return tok, [clip_l, clip_g, t5], clip_sd21
+
+
+TEXT_PROMPTS_FLAT = ["the car drives at night", "a red truck"]
+TEXT_PROMPTS_NESTED = [[["front %d" % t, "left %d" % t, "right %d" % t] for t in range(4)]]
+TEXT_CASES = {
+    # name -> (is_dit, prompts, text_condition_mask, cfg, drop T5)
+    "dit_flat_cfg": (True, TEXT_PROMPTS_FLAT, None, True, False),
+    "dit_nested_masked_cfg": (True, TEXT_PROMPTS_NESTED,
+                              [[[True, False, True], [True, True, True],
+                                [False, False, False], [True, True, False]]], True, False),
+    "dit_nested_no_t5": (True, TEXT_PROMPTS_NESTED, None, False, True),
+    "unet_nested": (False, TEXT_PROMPTS_NESTED, None, True, False),
+}
+
+
+def text_case_batch(name):
+    is_dit, prompts, mask, cfg, drop_t5 = TEXT_CASES[name]
+    B = len(prompts)
+    batch = {"pts": torch.zeros(B, 4, 3), "fps": torch.tensor([10.0] * B), "clip_text": prompts}
+    return batch, (B, 4, 3, 4, 2, 3)
+
+
+def tensor_fingerprint(t):
+    """Compact, order-sensitive signature of a tensor for JSON fixtures."""
+    f = t.detach().double().flatten()
+    idx = torch.linspace(0, f.numel() - 1, 64).long()
+    w = torch.arange(f.numel(), dtype=torch.float64) % 97 + 1
+    return {"shape": list(t.shape), "dtype": str(t.dtype), "sum": float(f.sum()),
+            "weighted": float((f * w).sum()), "abs": float(f.abs().sum()),
+            "samples": [float(v) for v in f[idx]]}
+
+
+def run_text_case(pipeline_cls, model_classes, name, stack):
+    """get_conditions text branch of `pipeline_cls` (reference or mirror) on a TEXT_CASES entry;
+    model_classes = (DiT-like class, UNet-like class) whose bare instances satisfy the
+    pipeline's isinstance checks."""
+    tok, encs, clip21 = stack
+    is_dit, prompts, mask, cfg, drop_t5 = TEXT_CASES[name]
+    batch, shape = text_case_batch(name)
+    model = object.__new__(model_classes[0] if is_dit else model_classes[1])
+    te = (encs[:2] + [None] if drop_t5 else encs) if is_dit else clip21
+    tk = [tok, tok, tok] if is_dit else tok
+    rc = pipeline_cls.get_conditions(model, te, tk, {}, shape, batch, "cpu", torch.float32,
+                                     text_condition_mask=mask, do_classifier_free_guidance=cfg)
+    return {k: tensor_fingerprint(rc[k]) for k in ("encoder_hidden_states", "pooled_projections")
+            if rc.get(k) is not None}

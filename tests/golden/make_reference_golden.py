@@ -17,7 +17,9 @@ touches -> the fp32 restatement in oracle/d31.py).  What runs from /root/referen
                                          StreamingCrossviewTemporalSD.reset_streaming +
                                          inference_pipeline (the diffusion-forcing loop, 3
                                          steps, CFG) and CrossviewTemporalSD.get_conditions /
-                                         get_camera_transform_ids / get_action_ids;
+                                         get_camera_transform_ids / get_action_ids, incl. its text
+                                         branch (flatten_clip_text, sd3_encode_prompt_with_clip,
+                                         sd3_encode_prompt_with_t5) on tiny seeded HF encoders;
                                          autoregressive_inference_pipeline (call traces with a
                                          stand-in inference_pipeline, four configurations);
                                          StreamingCrossviewTemporalSD.fifo_inference_pipeline /
@@ -46,7 +48,8 @@ import torch  # noqa: E402
 
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON,  # noqa: E402
                     FULL_SEQUENCE_CASES, TINY, VARIANTS, full_sequence_inputs,
-                    run_autoregressive_case, run_fifo_case,
+                    run_autoregressive_case, run_fifo_case, run_text_case, tiny_text_stack,
+                    TEXT_CASES,
                     condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
@@ -226,6 +229,16 @@ def main():
     # receive_frame / fifo_inference_pipeline with the real streaming-mode get_conditions
     traces["streaming_fifo"] = run_fifo_case(
         ref_pipe.StreamingCrossviewTemporalSD, object.__new__(diffusers.SD3Transformer2DModel))
+
+    # ---- text branch of get_conditions (flatten_clip_text, sd3_encode_prompt_with_clip / _t5,
+    #      CFG / mask handling, broadcast over frames and views) with tiny seeded HF encoders ------
+    stack = tiny_text_stack()
+    text = {name: run_text_case(
+        ref_pipe.CrossviewTemporalSD,
+        (diffusers.SD3Transformer2DModel, diffusers.UNetSpatioTemporalConditionModel), name, stack)
+        for name in TEXT_CASES}
+    with open(os.path.join(HERE, "reference_text_conditions.json"), "w") as f:
+        json.dump(text, f, indent=1)
 
     safetensors.torch.save_file(out, os.path.join(HERE, "reference_outputs.safetensors"))
     with open(os.path.join(HERE, "reference_autoregressive_traces.json"), "w") as f:

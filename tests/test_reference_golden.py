@@ -13,7 +13,8 @@ import torch
 
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, FULL_SEQUENCE_CASES,
                     TINY, VARIANTS, full_sequence_inputs,
-                    condition_batch, run_autoregressive_case, run_fifo_case,
+                    condition_batch, run_autoregressive_case, run_fifo_case, run_text_case,
+                    TEXT_CASES, tiny_text_stack,
                     scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -206,6 +207,34 @@ def test_mirror_streaming_fifo_matches_reference():
     for a, b in zip(got["calls"], want["calls"]):
         assert a == b
     assert got["images_shape"] == want["images_shape"] and got["images_sum"] == want["images_sum"]
+
+
+@pytest.fixture(scope="module")
+def text_stack():
+    return tiny_text_stack()
+
+
+@pytest.mark.parametrize("name", list(TEXT_CASES))
+def test_mirror_text_conditions_match_reference(name, text_stack):
+    """Prompts (`clip_text`) through real (tiny, seeded) CLIP / T5 encoders: nested prompt
+    flattening, CFG "" prompts, condition masks, CLIP-L|CLIP-G padding to the T5 width,
+    broadcast over frames / views — fingerprints of the tensors the reference's get_conditions
+    produced with the same encoder objects."""
+    import json
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.models.crossview_temporal_unet import UNetCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    with open(os.path.join(HERE, "golden", "reference_text_conditions.json")) as f:
+        want = json.load(f)[name]
+    got = run_text_case(CrossviewTemporalSD, (DiTCrossviewTemporalConditionModel,
+                                              UNetCrossviewTemporalConditionModel),
+                        name, text_stack)
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k]["shape"] == want[k]["shape"] and got[k]["dtype"] == want[k]["dtype"]
+        for f in ("sum", "weighted", "abs"):
+            assert got[k][f] == pytest.approx(want[k][f], rel=1e-6, abs=1e-6), (k, f)
+        assert got[k]["samples"] == pytest.approx(want[k]["samples"], rel=1e-5, abs=1e-6)
 
 
 def test_df_index_schedule_matches_reference_loop_arithmetic():
