@@ -1,17 +1,23 @@
-"""CTSD inference pipelines — mirror of the denoising part of reference
+"""CTSD inference pipelines — mirror of the inference part of reference
 src/dwm/pipelines/ctsd.py: `CrossviewTemporalSD` (ctor :844-1012, condition building
-:84-464) and `StreamingCrossviewTemporalSD` (diffusion-forcing FIFO :2010-2277).
+:84-464, `inference_pipeline` :1439-1654, `autoregressive_inference_pipeline` :1656-1833)
+and `StreamingCrossviewTemporalSD` (diffusion-forcing FIFO :2010-2277).
 
 Scope: the denoise loop, its integer timestep-index schedule, CFG
 batching, the model call and the scheduler update run on the B200-native kernels
 (`model.forward_tokens` + one fused CFG / un-patchify / per-frame-Euler / masked-update
-kernel per step, no host synchronisation inside the loop).  Training, evaluation,
-preview dumping and the text encoders are outside the hot path; text conditions are
-taken pre-encoded from the batch (`text_embeddings` / `pooled_text_embeddings` and
-their `uncond_*` twins for classifier-free guidance) because the CLIP/T5 checkpoints
-are not part of this implementation.  VAE decode happens when a `vae` object with
-the diffusers decode interface is supplied (`common_config["vae_instance"]`);
-otherwise the exiting latents are returned.
+kernel per step, no host synchronisation inside the loop); the VAE decode runs on the
+mirrored CogVideoX / AutoencoderKL decoders (loaded from `<path>/vae`, or supplied as
+`common_config["vae_instance"]`; without one the exiting latents are returned).
+Training, evaluation and preview dumping are not mirrored.  Text conditions come from the
+batch's `clip_text` prompts through Hugging Face CLIP / T5 when the checkpoint directory
+holds the encoders (`dwm.pipelines.text_conditions`, a caller of the hot path), or
+pre-encoded (`text_embeddings` / `pooled_text_embeddings` and their `uncond_*` twins for
+classifier-free guidance).
+
+The host logic is held to the reference's own code by `tests/test_reference_golden.py`
+(condition tensors, loop outputs and orchestration call traces recorded from
+/root/reference/src on a `diffusers` name shim).
 """
 import os
 
@@ -100,10 +106,11 @@ class CrossviewTemporalSD:
                        streaming_mode: bool = False, prev_ego_transforms=None,
                        do_classifier_free_guidance: bool = False,
                        latents_shape=None):
-        """Model kwargs from a data batch (reference :158-464).  `text_encoder` is
-        only a flag here: when not None the pre-encoded `text_embeddings`
-        [B,T,V,L,C] / `pooled_text_embeddings` [B,T,V,P] of the batch are used
-        (uncond half = `uncond_*` entries, or zeros when absent)."""
+        """Model kwargs from a data batch (reference :158-464).  Text: a batch with
+        pre-encoded `text_embeddings` [B,T,V,L,C] / `pooled_text_embeddings` [B,T,V,P] uses
+        them (uncond half = `uncond_*` entries, or zeros when absent; `text_encoder` then only
+        needs to be not None); a batch with `clip_text` prompts goes through the given
+        encoders / tokenizers like the reference does."""
         batch_size, _, view_count = latent_shape[:3]
         sequence_length = batch["pts"].shape[1]
         if do_classifier_free_guidance:
@@ -244,8 +251,8 @@ class CrossviewTemporalSD:
         self.model.enable_gradient_checkpointing()
         self.model.to(self.device)
 
-        # text encoders are not part of this implementation: a truthy marker keeps
-        # get_conditions on the "text provided" path when the batch is pre-encoded
+        # until real encoders are loaded below, a truthy marker keeps get_conditions on the
+        # "text provided" path for pre-encoded batches
         self.text_encoders = self.tokenizers = "pre-encoded"
         self._text_pending = pretrained_model_name_or_path
         self.vae = common_config.get("vae_instance")
