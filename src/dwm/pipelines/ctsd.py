@@ -407,7 +407,11 @@ class CrossviewTemporalSD:
         warm-up step on a scratch copy (lazy weight packing, condition caches, workspace)
         and captures."""
         stateful = not self.is_dit and not hasattr(self.test_scheduler, "final_alpha_cumprod")
-        if self.sharding is not None or stateful:      # multistep schedulers keep host state
+        # sharded steps contain NCCL / symmetric-memory exchanges: captured only on request
+        # (DWM_CUDA_GRAPH_SHARDED=1, not yet measured); multistep schedulers keep host state
+        sharded = self.sharding is not None and \
+            os.environ.get("DWM_CUDA_GRAPH_SHARDED", "0") != "1"
+        if sharded or stateful:
             return self.denoise_step(latents, conditions, idx, timesteps, in_range)
         key = (latents.data_ptr(), tuple(latents.shape), idx is None, in_range is None,
                tuple(sorted((k, v.data_ptr()) for k, v in conditions.items()
