@@ -98,6 +98,30 @@ class ShardPlan:
         dist.all_gather(parts, latents_local.contiguous(), group=self.t_group)
         return torch.cat(parts, dim=1)
 
+    def split_call(self, fn, items: torch.Tensor):
+        """Item-parallel map over ALL ranks (VAE decode: independent per (batch, view) clip or
+        per image): rank r applies `fn` to a contiguous share of
+        `items[n, ...]` and the results are all-gathered in order.  With more ranks than items
+        the surplus ranks contribute nothing (replicas only)."""
+        n = items.shape[0]
+        if self.world == 1 or n == 0:
+            return fn(items)
+        per = (n + self.world - 1) // self.world
+        lo, hi = min(self.rank * per, n), min((self.rank + 1) * per, n)
+        mine = fn(items[lo:hi]) if hi > lo else None
+        # every rank needs the output item shape; the rank holding item 0 announces it
+        meta = [None]
+        if self.rank == 0:
+            meta = [(tuple(mine.shape[1:]), mine.dtype)]
+        dist.broadcast_object_list(meta, src=0)
+        shape, dtype = meta[0]
+        pad = torch.zeros((per,) + shape, dtype=dtype, device=items.device)
+        if mine is not None:
+            pad[:hi - lo] = mine
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad)
+        return torch.cat(parts)[:n]
+
 
 class PeerKV:
     """Gathered K,V buffers of a frame group in symmetric (peer-mapped) memory.

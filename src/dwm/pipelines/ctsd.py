@@ -537,6 +537,16 @@ class CrossviewTemporalSD:
         ts_table = self.test_scheduler.timesteps.to(self.device).float()
         inject = (not df_mode) and image_latents is not None and \
             reference_frame_count > 0
+        # end-to-end sharding (opendwm_b200.sharding.ShardPlan in self.sharding): every rank
+        # builds the full noise / conditions (same generator seed), keeps its CFG branch and
+        # frames for the steps, and the window is re-assembled before the decode
+        plan = self.sharding if self.is_dit else None
+        fs = slice(0, T)
+        if plan is not None:
+            fs = plan.frame_slice()
+            conditions = plan.local_conditions(
+                conditions, cfg_doubled="guidance_scale" in self.inference_config)
+            latents = plan.local_latents(latents)
         # opt-in CUDA-graph replay of the step (inference_config["cuda_graph"] or env
         # DWM_CUDA_GRAPH=1): conditions are fixed for the whole window here
         use_graph = self.inference_config.get(
@@ -557,19 +567,27 @@ class CrossviewTemporalSD:
             if inject:
                 # reference frames enter clean at timestep 0 and are restored after
                 # the update, which reproduces the reference's per-step re-injection
-                ref = image_latents[:, :reference_frame_count].to(latents)
-                latents[:, :reference_frame_count] = ref
                 timesteps = timesteps.clone()
                 timesteps[:, :reference_frame_count] = 0
+                n_loc = max(0, min(reference_frame_count, fs.stop) - fs.start)
+                if n_loc > 0:
+                    latents[:, :n_loc] = image_latents[:, fs.start:fs.start + n_loc].to(latents)
+            if plan is not None:
+                idx, timesteps = idx[:, fs].contiguous(), timesteps[:, fs].contiguous()
+                in_range = None if in_range is None else in_range[fs].contiguous()
             step(latents, conditions, idx, timesteps, in_range)
+        if plan is not None:
+            latents = plan.gather_latents(latents)
+        decode = self.decode_latents if plan is None or self.vae is None else \
+            (lambda t: plan.split_call(self.decode_latents, t))
         if df_mode:
             cur = latents[:, take_time].flatten(0, 1)
             if self.is_temporal_vae and self.vae is not None:
                 cur = torch.cat([cur[:, :, None], cur[:, :, None] * 0], dim=2)
-                image_tensor = self.decode_latents(cur).chunk(2, dim=2)[0]
+                image_tensor = decode(cur).chunk(2, dim=2)[0]
                 image_tensor = image_tensor.permute(0, 2, 1, 3, 4).flatten(0, 1)
             else:
-                image_tensor = self.decode_latents(cur)
+                image_tensor = decode(cur)
         else:
             if image_latents is not None:
                 latents = torch.cat([
@@ -580,7 +598,8 @@ class CrossviewTemporalSD:
                 # "b t v c h w -> (b v) c t h w"
                 cur = latents.permute(0, 2, 3, 1, 4, 5).flatten(0, 1)
                 image_tensor = dwm.functional.memory_efficient_split_call(
-                    self, cur, lambda blk, t: blk.decode_latents(t), split)
+                    self, cur, lambda blk, t: blk.decode_latents(t), split) \
+                    if plan is None else decode(cur)
                 # "(b v) c t h w -> (b t v) c h w"
                 Tn = image_tensor.shape[2]
                 image_tensor = image_tensor.view(B, V, -1, Tn, *image_tensor.shape[-2:])\
@@ -588,7 +607,8 @@ class CrossviewTemporalSD:
             else:
                 image_tensor = dwm.functional.memory_efficient_split_call(
                     self, latents.flatten(0, 2),
-                    lambda blk, t: blk.decode_latents(t), split)
+                    lambda blk, t: blk.decode_latents(t), split) \
+                    if plan is None else decode(latents.flatten(0, 2))
         images = image_tensor if self.vae is None else \
             CrossviewTemporalSD.postprocess(image_tensor, output_type)
         return {"images": images, "latents": latents}

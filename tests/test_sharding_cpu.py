@@ -101,3 +101,93 @@ def test_plan_shapes_without_groups():
         ShardPlan(8, 0, 6, make_groups=False)
     p1 = ShardPlan(1, 0, 16, make_groups=False)
     assert (p1.cfg_ways, p1.t_ways, p1.T_loc) == (1, 1, 16)
+
+
+# -- end-to-end sharded window: inference_pipeline with a ShardPlan (slices, per-step index
+#    tensors, reference frames crossing shard boundaries, latent gather, item-parallel decode) ----
+
+class _FakeVae:
+    class config:
+        scaling_factor, shift_factor = 0.5, 0.25
+    dtype = torch.float32
+
+    def __init__(self, temporal):
+        self.temporal = temporal
+
+    def decode(self, x, return_dict=False):
+        if self.temporal:            # [(b v), c, t, h, w] -> 1 + 4 (t - 1) frames
+            t_out = 1 + 4 * (x.shape[2] - 1) if x.shape[2] > 1 else 1
+            x = x[:, :3].repeat_interleave(4, dim=2)[:, :, :t_out] if x.shape[2] > 1 else x[:, :3]
+        else:
+            x = x[:, :3]
+        return (x * 2 + 1,)
+
+
+def _window_pipe(plan, df, temporal):
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    pipe = object.__new__(CrossviewTemporalSD)
+    pipe.common_config = {"frame_prediction_style": "diffusion_forcing" if df else "ctsd",
+                          "condition_on_all_frames": True, "added_time_ids": "fps_camera_transforms",
+                          "camera_intrinsic_embedding_indices": [0, 4, 2, 5],
+                          "camera_intrinsic_denom_embedding_indices": [1, 1, 0, 1],
+                          "camera_transform_embedding_indices": [2, 6, 10, 3, 7, 11]}
+    pipe.inference_config = {"guidance_scale": 2.0, "inference_steps": 8,
+                             "sequence_length_per_iteration": 4}
+    pipe.device, pipe.model_dtype = torch.device("cpu"), torch.float32
+    pipe.generator = torch.Generator().manual_seed(0)
+    pipe.model = object.__new__(DiTCrossviewTemporalConditionModel)
+    pipe.text_encoders = pipe.tokenizers = None
+    pipe.is_dit, pipe.is_temporal_vae, pipe.vae = True, temporal, _FakeVae(temporal)
+    pipe.sharding, pipe._step_cache = plan, {}
+    pipe.test_scheduler = type("S", (), {
+        "timesteps": torch.linspace(1000, 100, 8), "num_inference_steps": 8,
+        "init_noise_sigma": 1.0, "set_timesteps": lambda self, n, device=None: None})()
+
+    def fake_step(latents, conditions, idx, timesteps, in_range=None):
+        # frame-local update from quantities both CFG branches share
+        cam = conditions["camera_transforms"][:latents.shape[0]].sum((-1, -2))
+        upd = timesteps.float() / 1000 + 1e-2 * cam + 1e-3 * idx.float()
+        new = latents * 0.9 + upd[..., None, None, None]
+        if in_range is not None:
+            new = torch.where(in_range.bool().view(1, -1, 1, 1, 1, 1), new, latents)
+        latents.copy_(new)
+        return latents
+    pipe.denoise_step = fake_step
+    return pipe
+
+
+def _sharded_window(rank, world):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import condition_batch
+    from opendwm_b200.sharding import ShardPlan
+    T, V = 4, 3
+    shape = (1, T, V, 4, 2, 3)
+    plan = ShardPlan(world, rank, T, cfg=True)
+    batch = condition_batch(T=T, V=V)
+    ref_lat = torch.randn(shape, generator=torch.Generator().manual_seed(5))
+    cases = [dict(df=False, temporal=False, kw={}),
+             dict(df=False, temporal=False, kw=dict(image_latents=ref_lat, reference_frame_count=1)),
+             dict(df=False, temporal=True, kw=dict(image_latents=ref_lat, reference_frame_count=3,
+                                                  start_timestep=2, stop_timestep=7)),
+             dict(df=True, temporal=False, kw=dict(image_latents=ref_lat, start_timestep=3,
+                                                   stop_timestep=6, take_time=1)),
+             dict(df=True, temporal=True, kw={})]
+    for c in cases:
+        want = _window_pipe(None, c["df"], c["temporal"]).inference_pipeline(
+            shape, batch, "pt", **c["kw"])
+        got = _window_pipe(plan, c["df"], c["temporal"]).inference_pipeline(
+            shape, batch, "pt", **c["kw"])
+        assert got["latents"].shape == want["latents"].shape
+        assert torch.equal(got["latents"], want["latents"]), (rank, c)
+        assert got["images"].shape == want["images"].shape
+        assert torch.equal(got["images"], want["images"]), (rank, c)
+
+
+def test_sharded_window_matches_unsharded_world2():
+    _run(_sharded_window, 2)          # cfg2 x frames1
+
+
+def test_sharded_window_matches_unsharded_world4():
+    _run(_sharded_window, 4)          # cfg2 x frames2, decode of 3 items over 4 ranks
