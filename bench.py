@@ -346,7 +346,10 @@ def run_native(args):
                 "h2d_bytes_per_step": latents_host.numel() * 4 + idx_host[0].numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4,
                 "api": "StreamingCrossviewTemporalSD.denoise_step with pinned host "
-                       "latents + index tensors copied in and latents copied out"},
+                       "latents + index tensors copied in and latents copied out; a separate "
+                       "timed loop (the device-resident loop above also records one CUDA-event "
+                       "pair around each of its GEMM launches for the roofline, this one does "
+                       "not, which is why it can come out marginally faster)"},
         "gpu_launches": prof["launches"],
         "clocks": clocks,
     }
