@@ -58,6 +58,25 @@ def _attention(channels, groups):
     return m
 
 
+class DiagonalGaussianDistribution:
+    """mean | logvar along channels (diffusers vae.py)."""
+
+    def __init__(self, parameters):
+        self.parameters = parameters
+        self.mean, logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(logvar, -30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator,
+                            device=self.mean.device if generator is None or
+                            generator.device.type == "cuda" else "cpu").to(self.mean)
+        return self.mean + self.std * noise
+
+
 class AutoencoderKL(torch.nn.Module):
 
     def __init__(self, in_channels=3, out_channels=3, down_block_types=None,
@@ -74,7 +93,8 @@ class AutoencoderKL(torch.nn.Module):
             in_channels=in_channels, out_channels=out_channels, block_out_channels=boc,
             layers_per_block=layers_per_block, latent_channels=latent_channels,
             norm_num_groups=norm_num_groups, scaling_factor=scaling_factor,
-            shift_factor=shift_factor, use_post_quant_conv=use_post_quant_conv,
+            shift_factor=shift_factor, use_quant_conv=use_quant_conv,
+            use_post_quant_conv=use_post_quant_conv,
             mid_block_add_attention=mid_block_add_attention,
             down_block_types=tuple(down_block_types or ("DownEncoderBlock2D",) * len(boc)))
         self.compute_dtype = compute_dtype
@@ -106,7 +126,33 @@ class AutoencoderKL(torch.nn.Module):
         self.decoder = d
         if use_post_quant_conv:
             self.post_quant_conv = torch.nn.Conv2d(latent_channels, latent_channels, 1)
+        # encoder (reference-frame conditioning, ctsd.py:1681-1700): same building blocks
+        e = _P()
+        e.conv_in = torch.nn.Conv2d(in_channels, boc[0], 3, padding=1)
+        e.down_blocks = torch.nn.ModuleList()
+        out = boc[0]
+        for i, ch in enumerate(boc):
+            prev, out = out, ch
+            b = _P()
+            b.resnets = torch.nn.ModuleList(
+                [_resnet(prev if j == 0 else out, out, g) for j in range(layers_per_block)])
+            if i != len(boc) - 1:
+                dn = _P()
+                dn.conv = torch.nn.Conv2d(out, out, 3, stride=2, padding=0)
+                b.downsamplers = torch.nn.ModuleList([dn])
+            e.down_blocks.append(b)
+        e.mid_block = _P()
+        e.mid_block.resnets = torch.nn.ModuleList(
+            [_resnet(boc[-1], boc[-1], g), _resnet(boc[-1], boc[-1], g)])
+        e.mid_block.attentions = torch.nn.ModuleList(
+            [_attention(boc[-1], g)] if mid_block_add_attention else [])
+        e.conv_norm_out = torch.nn.GroupNorm(g, boc[-1], eps=1e-6)
+        e.conv_out = torch.nn.Conv2d(boc[-1], 2 * latent_channels, 3, padding=1)
+        self.encoder = e
+        if use_quant_conv:
+            self.quant_conv = torch.nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
         self._pk = None
+        self._pk_enc = None
 
     # -- diffusers-style plumbing -------------------------------------------------------
     @property
@@ -135,25 +181,31 @@ class AutoencoderKL(torch.nn.Module):
         return vae
 
     def _apply(self, fn, *a, **k):
-        self._pk = None
+        self._pk = self._pk_enc = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        """Encoder-side keys of a full VAE checkpoint are dropped (decode only); the
-        pre-0.20 attention names (query/key/value/proj_attn) are accepted like diffusers'
-        `_convert_deprecated_attention_blocks` does."""
-        self._pk = None
+        """Accepts full VAE checkpoints and decoder-only ones (missing encoder / quant_conv
+        keys keep their initial values); the pre-0.20 attention names (query/key/value/
+        proj_attn) are accepted like diffusers' `_convert_deprecated_attention_blocks` does."""
+        self._pk = self._pk_enc = None
         ren = {"query": "to_q", "key": "to_k", "value": "to_v", "proj_attn": "to_out.0"}
         sd = {}
         for k, v in state_dict.items():
-            if k.startswith("encoder.") or k.startswith("quant_conv."):
-                continue
             parts = k.split(".")
             if "attentions" in parts and parts[-2] in ren:
                 k = ".".join(parts[:-2] + [ren[parts[-2]], parts[-1]])
                 if v.dim() == 4:
                     v = v.flatten(1)
             sd[k] = v
+        own = super().state_dict()
+        sd = {k: v for k, v in sd.items() if k in own or
+              not (k.startswith("encoder.") or k.startswith("quant_conv."))}
+        decoder_only = not any(k.startswith("encoder.") for k in sd)
+        if decoder_only:
+            for k, v in own.items():
+                if k.startswith("encoder.") or k.startswith("quant_conv."):
+                    sd.setdefault(k, v)
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     # -- weight packing --------------------------------------------------------------------
@@ -271,6 +323,115 @@ class AutoencoderKL(torch.nn.Module):
             _ops.softmax_rows(s, scale, pr)
             _ops.linear(pr, vt[:, r], out=o[r])
         return _ops.linear(o, p["wo"], p["bo"], epilogue=_lib.EPI_RESID, resid=h)
+
+    # -- encoder ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _pack_encoder(self):
+        """Packed separately (first `encode`), so the decode path never depends on it."""
+        e = self.encoder
+        dev = e.conv_in.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("AutoencoderKL.encode runs on CUDA (sm_100a) only; there is no "
+                               "CPU fallback.")
+        dt = self.compute_dtype
+
+        def conv3(c, pad_in=None, pad_out=None):
+            w = _ops.pack_conv_weight(c.weight.to(dev), dt, pad_out_to=pad_out, pad_in_to=pad_in)
+            b = torch.zeros(w.shape[1], device=dev)
+            b[:c.out_channels] = c.bias.detach().float()
+            return w, b
+
+        def lin(weight, bias):
+            return (weight.detach().reshape(weight.shape[0], -1).to(dev, dt).contiguous(),
+                    bias.detach().float().to(dev).contiguous())
+
+        def gn(n):
+            return (n.weight.detach().float().to(dev).contiguous(),
+                    n.bias.detach().float().to(dev).contiguous())
+
+        def res(m):
+            p = dict(n1=gn(m.norm1), c1=conv3(m.conv1), n2=gn(m.norm2), c2=conv3(m.conv2))
+            if hasattr(m, "conv_shortcut"):
+                p["sc"] = lin(m.conv_shortcut.weight, m.conv_shortcut.bias)
+            return p
+        pk = dict(conv_in=conv3(e.conv_in, pad_in=8), downs=[])
+        for blk in e.down_blocks:
+            b = dict(res=[res(r) for r in blk.resnets])
+            if hasattr(blk, "downsamplers"):
+                b["down"] = conv3(blk.downsamplers[0].conv)
+            pk["downs"].append(b)
+        pk["mid"] = [res(r) for r in e.mid_block.resnets]
+        pk["attn"] = None
+        if len(e.mid_block.attentions):
+            a = e.mid_block.attentions[0]
+            wq, bq = lin(a.to_q.weight, a.to_q.bias)
+            wk, bk = lin(a.to_k.weight, a.to_k.bias)
+            wv, bv = lin(a.to_v.weight, a.to_v.bias)
+            wo, bo = lin(a.to_out[0].weight, a.to_out[0].bias)
+            bo = bo + a.to_out[0].weight.detach().float().to(dev) @ bv
+            pk["attn"] = dict(gn=gn(a.group_norm), wqk=torch.cat([wq, wk]).contiguous(),
+                              bqk=torch.cat([bq, bk]).contiguous(), wv=wv, wo=wo,
+                              bo=bo.contiguous())
+        pk["norm_out"] = gn(e.conv_norm_out)
+        lc2 = 2 * self.config.latent_channels
+        cq = (lc2 + 31) // 32 * 32
+        pk["conv_out"] = conv3(e.conv_out, pad_out=cq)
+        if hasattr(self, "quant_conv"):
+            w = torch.zeros(cq, cq, device=dev, dtype=dt)
+            w[:lc2, :lc2] = self.quant_conv.weight.detach().reshape(lc2, lc2).to(dev, dt)
+            b = torch.zeros(cq, device=dev)
+            b[:lc2] = self.quant_conv.bias.detach().float()
+            pk["quant"] = (w, b)
+        self._pk_enc = pk
+        return pk
+
+    @torch.no_grad()
+    def encode(self, x, return_dict: bool = True):
+        """x: [n, 3, H, W] images in [-1, 1] -> `.latent_dist` with `mode()` / `sample()`
+        (reference ctsd.py:1689-1700: `vae.encode(t).latent_dist.mode()`).  The stride-2
+        down-sampling convolutions (right / bottom zero padding, no left / top padding) run as
+        stride-1 'same' convolutions whose odd output positions are kept."""
+        if not x.is_cuda:
+            raise RuntimeError("AutoencoderKL.encode needs CUDA tensors; there is no CPU "
+                               "fallback.")
+        pk = self._pk_enc or self._pack_encoder()
+        dt = self.compute_dtype
+        nb, cin, H, W = x.shape
+        if H % 2 ** (len(pk["downs"]) - 1) or W % 2 ** (len(pk["downs"]) - 1):
+            raise ValueError("image size must be divisible by the VAE down-sampling factor")
+        x16 = torch.zeros(nb, 1, H, W, pk["conv_in"][0].shape[2], device=x.device, dtype=dt)
+        x16[..., :cin] = x.permute(0, 2, 3, 1).unsqueeze(1)
+        h = _ops.conv(x16, *pk["conv_in"], kernel=(1, 3, 3), epilogue=_lib.EPI_F32)
+        shape = (nb, H, W)
+        for blk in pk["downs"]:
+            for p in blk["res"]:
+                h = self._resnet(h, shape, p)
+            if "down" in blk:
+                n, H, W = shape
+                h16 = torch.empty(h.shape, device=h.device, dtype=dt)
+                _ops.act_cast(h, h16)
+                y = _ops.conv(h16.view(n, 1, H, W, -1), *blk["down"], kernel=(1, 3, 3),
+                              epilogue=_lib.EPI_F32)
+                C = y.shape[1]
+                h = y.view(n, H, W, C)[:, 1::2, 1::2].contiguous().view(-1, C)
+                shape = (n, H // 2, W // 2)
+        h = self._resnet(h, shape, pk["mid"][0])
+        if pk["attn"] is not None:
+            h = self._attn(h, shape, pk["attn"])
+        h = self._resnet(h, shape, pk["mid"][1])
+        a = self._norm(h, shape, pk["norm_out"], True)
+        if "quant" in pk:
+            m16 = _ops.conv(a, *pk["conv_out"], kernel=(1, 3, 3), epilogue=_lib.EPI_STORE)
+            moments = _ops.linear(m16, *pk["quant"], epilogue=_lib.EPI_F32)
+        else:
+            moments = _ops.conv(a, *pk["conv_out"], kernel=(1, 3, 3), epilogue=_lib.EPI_F32)
+        n, H, W = shape
+        lc = self.config.latent_channels
+        moments = moments.view(n, H, W, -1)[..., :2 * lc].permute(0, 3, 1, 2).contiguous()
+        dist = DiagonalGaussianDistribution(moments.to(x.dtype))
+        if not return_dict:
+            return (dist,)
+        return _Cfg(latent_dist=dist)
 
     # -- public API ------------------------------------------------------------------------------
     @torch.no_grad()

@@ -646,12 +646,24 @@ class CrossviewTemporalSD:
         win = inf["sequence_length_per_iteration"]
         n_ref = inf.get("reference_frame_count", 1)
         df_mode = self.common_config.get("frame_prediction_style") == "diffusion_forcing"
-        if not inf.get("generate_frames_for_reference", True):
-            raise NotImplementedError(
-                "reference frames from batch[\"vae_images\"] need the VAE encoder, which is "
-                "outside this implementation (SURVEY.md §8(f)3); leave "
-                "generate_frames_for_reference at its default")
         image_latents = None
+        if not inf.get("generate_frames_for_reference", True):
+            # reference frames from real images: VAE-encode batch["vae_images"] (reference
+            # :1677-1700).  Image VAEs only; the temporal-VAE encoder is not mirrored.
+            if self.is_temporal_vae or not hasattr(self.vae, "encode"):
+                raise NotImplementedError(
+                    "reference frames from batch[\"vae_images\"] need a VAE encoder; only the "
+                    "2-D AutoencoderKL encoder is provided (SURVEY.md §8(f)3)")
+            raw = batch["vae_images"][:, :n_ref]
+            x = raw.flatten(0, 2).to(self.device) * 2 - 1        # VaeImageProcessor.preprocess
+            shift = self.vae.config.shift_factor \
+                if self.vae.config.shift_factor is not None else 0
+            enc = dwm.functional.memory_efficient_split_call(
+                self.vae, x.to(dtype=self.vae.dtype),
+                lambda block, t: (block.encode(t).latent_dist.mode() - shift) *
+                block.config.scaling_factor,
+                self.common_config.get("memory_efficient_batch", -1))
+            image_latents = enc.unflatten(0, raw.shape[:3])
         images = []
         stride = win - n_ref
         starts = range(0, n_total - win + 1, stride)
@@ -681,7 +693,7 @@ class CrossviewTemporalSD:
             # warm-up: bring the queue to the staggered steady state
             window = self._window(batch, 0, win)
             image_latents = self.inference_pipeline(
-                latent_shape, window, output_type, None, reference_frame_count=0,
+                latent_shape, window, output_type, image_latents, reference_frame_count=0,
                 start_timestep=0, stop_timestep=steps - spi)["latents"]
             head = -1
             for i in starts:

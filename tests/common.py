@@ -191,6 +191,11 @@ AUTOREGRESSIVE_CASES = {
                            "reference_frame_count": 1, "vae_pre": 1, "vae_stride": 4,
                            "generate_frames_for_reference": True},
                           (1, 5, 3, 4, 2, 3), 33, True),
+    "windows_encoded_reference": ({"frame_prediction_style": "ctsd", "memory_efficient_batch": 4},
+                                  {"inference_steps": 8, "sequence_length_per_iteration": 6,
+                                   "reference_frame_count": 2,
+                                   "generate_frames_for_reference": False},
+                                  (1, 6, 3, 4, 2, 3), 14, False),
     "diffusion_forcing": ({"frame_prediction_style": "diffusion_forcing"},
                           {"inference_steps": 12, "sequence_length_per_iteration": 4,
                            "autoregression_data_exception_for_take_sequence":
@@ -204,8 +209,24 @@ AUTOREGRESSIVE_CASES = {
 }
 
 
+class _TraceVae:
+    """Stand-in image VAE for the orchestration traces (encode = subsample, no arithmetic of a
+    real VAE): `.encode(x).latent_dist.mode()`, `.config`, `.dtype`."""
+    class config:
+        scaling_factor, shift_factor = 0.5, 0.25
+    dtype = torch.float32
+
+    @staticmethod
+    def encode(x):
+        z = torch.cat([x, x[:, :1]], 1)[:, :, ::8, ::8]
+        dist = type("D", (), {"mode": lambda self: z})()
+        return type("O", (), {"latent_dist": dist})()
+
+
 def autoregressive_batch(n_frames, V=3):
+    g = torch.Generator().manual_seed(77)
     return {"pts": torch.arange(n_frames).float().view(1, n_frames, 1).repeat(1, 1, V),
+            "vae_images": torch.rand(1, n_frames, V, 3, 16, 24, generator=g),
             "fps": torch.tensor([10.0]),
             "crossview_mask": torch.ones(1, V, V, dtype=torch.bool),
             "clip_text": [["frame %d" % t for t in range(n_frames)]]}
@@ -248,6 +269,8 @@ def run_autoregressive_case(cls, name):
     pipe.generator = torch.Generator().manual_seed(0)
     pipe.is_temporal_vae = temporal
     pipe.test_scheduler = type("S", (), {"init_noise_sigma": 1.0})()
+    pipe.vae = _TraceVae()
+    pipe.image_processor = type("P", (), {"preprocess": staticmethod(lambda t: 2.0 * t - 1.0)})()
     trace = []
     install_fake_inference_pipeline(pipe, trace)
     out = pipe.autoregressive_inference_pipeline(shape, autoregressive_batch(n_frames), "pt")

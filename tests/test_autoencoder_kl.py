@@ -41,11 +41,13 @@ def test_state_dict_and_loader_cpu(tmp_path):
         assert set(so) == set(sm), sorted(set(so) ^ set(sm))[:8]
         for k in so:
             assert so[k].shape == sm[k].shape, k
-        # a full checkpoint also carries encoder / quant_conv weights: ignored
-        full = dict(so)
-        full["encoder.conv_in.weight"] = torch.zeros(1)
-        full["quant_conv.weight"] = torch.zeros(1)
-        m.load_state_dict(full, strict=True)
+        m.load_state_dict(so, strict=True)                  # full checkpoint
+        # a decoder-only checkpoint loads too (encoder keeps its initial weights)
+        dec_only = {k: v for k, v in so.items()
+                    if not (k.startswith("encoder.") or k.startswith("quant_conv."))}
+        m2 = AutoencoderKL(**cfg)
+        m2.load_state_dict(dec_only, strict=True)
+        assert torch.equal(m2.decoder.conv_in.weight, so["decoder.conv_in.weight"])
     # pre-0.20 attention names with 1x1-conv shaped weights
     old = {}
     for k, v in _oracle(SD21).state_dict().items():
@@ -72,6 +74,8 @@ def test_state_dict_and_loader_cpu(tmp_path):
     assert not hasattr(v, "post_quant_conv")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         v.decode(torch.zeros(1, 16, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        v.encode(torch.zeros(1, 3, 64, 64))
 
 
 @pytest.mark.gpu
@@ -111,3 +115,30 @@ def test_softmax_rows():
         ref = torch.softmax(xs * 0.37, dim=-1)
         assert (out.float() - ref).abs().max().item() < (4e-3 if dt == torch.bfloat16 else 5e-4)
         assert abs(out.float().sum(-1) - 1).max().item() < 2e-2
+
+
+# GPU validation pending: written after the round's GPU budget was spent.  Opt in with
+# DWM_RUN_UNVALIDATED=1 (first thing to run next round).
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("DWM_RUN_UNVALIDATED", "0") != "1",
+                    reason="encode path not yet run on a GPU (set DWM_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("name,dtype,tol", [("sd35", torch.float16, 6e-3),
+                                            ("sd21", torch.float16, 6e-3)])
+def test_encode_matches_oracle(name, dtype, tol):
+    from dwm.models.autoencoder_kl import AutoencoderKL
+    cfg = SD35 if name == "sd35" else SD21
+    o = _oracle(cfg).cuda()
+    m = AutoencoderKL(**cfg, compute_dtype=dtype)
+    m.load_state_dict(o.state_dict())
+    m.cuda()
+    g = torch.Generator().manual_seed(5)
+    up = 2 ** (len(cfg["block_out_channels"]) - 1)
+    x = (torch.rand(3, 3, 8 * up, 12 * up, generator=g) * 2 - 1).cuda()
+    with torch.no_grad():
+        ref = o.encode(x.to(dtype).float()).latent_dist
+    d = m.encode(x.to(dtype)).latent_dist
+    assert d.mode().shape == ref.mode().shape == (3, cfg["latent_channels"], 8, 12)
+    err = ((d.mode().float() - ref.mode()).abs().max() / ref.mode().abs().max()).item()
+    assert err < tol, err
+    err = ((d.std.float() - ref.std).abs().max() / ref.std.abs().max()).item()
+    assert err < 5 * tol, err
