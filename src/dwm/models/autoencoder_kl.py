@@ -354,7 +354,7 @@ class AutoencoderKL(torch.nn.Module):
             if hasattr(m, "conv_shortcut"):
                 p["sc"] = lin(m.conv_shortcut.weight, m.conv_shortcut.bias)
             return p
-        pk = dict(conv_in=conv3(e.conv_in, pad_in=8), downs=[])
+        pk = dict(conv_in=conv3(e.conv_in, pad_in=16), downs=[])   # 16 = smallest validated C_in
         for blk in e.down_blocks:
             b = dict(res=[res(r) for r in blk.resnets])
             if hasattr(blk, "downsamplers"):
