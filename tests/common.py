@@ -328,6 +328,9 @@ FULL_SEQUENCE_CASES = {
     "plain": ({"guidance_scale": 3.0, "inference_steps": 3}, 0),
     "reference_frames": ({"guidance_scale": 3.0, "inference_steps": 3}, 1),
     "no_cfg_partial": ({"inference_steps": 4}, 0),
+    # diffusion-forcing branch of the NON-streaming class (what the autoregressive loop calls):
+    # queue given as image_latents, partial step range, emitted frame = queue slot take_time
+    "df_queue_partial": ({"guidance_scale": 2.0, "inference_steps": 6}, 0),
 }
 
 

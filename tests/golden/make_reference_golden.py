@@ -174,6 +174,10 @@ def main():
         kw = dict(image_latents=f_image_latents, reference_frame_count=nref) if nref else {}
         if name == "no_cfg_partial":
             kw.update(start_timestep=1, stop_timestep=3)
+        if name == "df_queue_partial":
+            fp.common_config = dict(fcommon, frame_prediction_style="diffusion_forcing")
+            kw = dict(image_latents=f_image_latents, reference_frame_count=3, start_timestep=2,
+                      stop_timestep=4, take_time=1)
         P.get_conditions = staticmethod(gc_with_text)
         try:
             with torch.no_grad():
