@@ -102,7 +102,8 @@ typedef struct dwm_linear_args {
 
 const char* dwm_b200_version(void);
 const char* dwm_b200_last_error(void);
-/* Runtime switches: "gemm_2cta" = 1 routes dwm_b200_linear (M >= 512) to the 2-CTA
+/* Runtime switches (no reference counterpart; they select between kernels that must agree,
+ * which tests/ use for kernel-variant parity): "gemm_2cta" = 1 routes dwm_b200_linear (M >= 512) to the 2-CTA
  * cta_group::2 kernel, 0 to the 1-CTA kernel (default: env DWM_GEMM_2CTA, else 1);
  * "attn_tc" routes eligible (contiguous, unmasked, head_dim 64) attention: 2 = tcgen05
  * kernel with two co-resident CTAs per SM and O in TMEM (default), 1 = first-generation
@@ -205,7 +206,9 @@ typedef struct dwm_layernorm_args {
 
 int dwm_b200_layernorm(const dwm_layernorm_args* args, dwm_stream_t stream);
 
-/* out16[i] = act(in32[i]) over n elements (e.g. SiLU(temb) feeding AdaLayerNormZero.linear). */
+/* out16[i] = act(in32[i]) over n elements: SiLU(temb) feeding the AdaLayerNormZero linears of
+ * the joint blocks (called at crossview_temporal_dit.py:517-521) and the UNet ResBlock
+ * time_emb_proj (crossview_temporal.py:104-113); plain 16-bit casts of GEMM / conv operands. */
 int dwm_b200_act_cast(const float* in, void* out, int64_t n, int act, int dtype, dwm_stream_t stream);
 
 /* diffusers Timesteps(num_channels, flip_sin_to_cos, downscale_freq_shift): sinusoidal
@@ -281,17 +284,22 @@ typedef struct dwm_conv_args {
 
 int dwm_b200_conv(const dwm_conv_args* args, dwm_stream_t stream);
 
-/* ---- CogVideoX temporal-VAE decoder row kernels (channels-last fp32 activations) ------- */
+/* ---- GroupNorm / SpatialNorm3D / upsampling pixel kernels (channels-last fp32 activations) of
+ * the VAE decoders the reference calls at src/dwm/pipelines/ctsd.py:1609-1643, 2095-2098 and of
+ * the UNet ResBlocks / TransformerModel (src/dwm/models/crossview_temporal.py:75-164, 288-289) -- */
 /* GroupNorm statistics: sums[n][g] = (sum, sum of squares) over the C/groups channels of
  * group g and all `pixels` (= T*H*W) of volume n; `sums` (double [nb, groups, 2]) is zeroed
- * here.  (diffusers CogVideoXSpatialNorm3D.norm_layer; statistics are per decode chunk.) */
+ * here.  (torch.nn.GroupNorm in ResnetBlock2D / TemporalResnetBlock, crossview_temporal.py:104-113;
+ * diffusers CogVideoXSpatialNorm3D.norm_layer, where statistics are per decode chunk.) */
 int dwm_b200_groupnorm_stats(const float* x, int64_t nb, int64_t pixels, int C, int groups,
                              double* sums, dwm_stream_t stream);
 /* out16[n, out_t0 + t, h, w, c] = act( GN(x)*gamma+beta [ * zy[nearest] + zb[nearest] ] )
  * with zy = conv_y(zq), zb = conv_b(zq) given at the latent resolution [nb, Tz, hz, wz, C]
  * (nearest-neighbour lookup, first frame mapped separately when T is odd > 1).  Writes
  * into a 16-bit channels-last buffer of out_T frames at frame offset out_t0 (the leading
- * frames hold the causal-conv cache).  zy = zb = NULL gives plain GroupNorm (+SiLU). */
+ * frames hold the causal-conv cache).  zy = zb = NULL gives plain GroupNorm (+SiLU), the
+ * `norm -> nonlinearity` prefix of every ResBlock convolution (crossview_temporal.py:126-158)
+ * and of `conv_norm_out -> conv_act` (crossview_temporal_unet.py:815-817). */
 int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
                               int groups, const double* sums, float eps, const float* gamma,
                               const float* beta, const float* zy, const float* zb, int Tz, int hz,
@@ -299,7 +307,8 @@ int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, int64_t H, 
                               int dtype, dwm_stream_t stream);
 /* CogVideoXUpsample3D interpolation: nearest x2 in H, W and (compress_time) in T, where an
  * odd T > 1 keeps its first frame un-doubled in time; fp32 in, 16-bit out
- * [nb, T', 2H, 2W, C]. */
+ * [nb, T', 2H, 2W, C].  Also the F.interpolate(nearest, x2) of the UNet / AutoencoderKL
+ * up-samplers (crossview_temporal_unet.py:263-266, 347-350). */
 int dwm_b200_upsample_nearest(const float* x, int64_t nb, int64_t T, int64_t H, int64_t W, int C,
                               int compress_time, void* out, int dtype, dwm_stream_t stream);
 
