@@ -725,6 +725,62 @@ class CrossviewTemporalSD:
         return {"images": torch.cat(images) if output_type == "pt" else images}
 
 
+    # -- entry point of src/dwm/preview.py ------------------------------------------------------
+    def _preview_latent_shape(self, batch, frames):
+        """[B, latent frames, V, C, h, w] from the batch's image size and the VAE config
+        (reference :1839-1862, :2283-2294)."""
+        B, _, V = batch["vae_images"].shape[:3]
+        down = 2 ** (len(self.vae.config.down_block_types) - 1)
+        return (B, frames, V, self.vae.config.latent_channels,
+                batch["vae_images"].shape[-2] // down, batch["vae_images"].shape[-1] // down)
+
+    def _dump_preview(self, images, batch, output_path, global_step):
+        """Writes <output_path>/preview/<step>.png|.mp4 through the reference's
+        dwm.utils.preview (PyAV based, not part of this mirror) when it is importable — i.e.
+        when these files are overlaid on the reference tree — and PNG frames otherwise."""
+        import torchvision
+        all_rank = self.inference_config.get("all_rank_preview", False)
+        if not (self.should_save or (torch.distributed.is_initialized() and all_rank)):
+            return
+        folder = os.path.join(output_path, "preview")
+        os.makedirs(folder, exist_ok=True)
+        name = "{}_{}".format(global_step, torch.distributed.get_rank()) if all_rank \
+            else str(global_step)
+        frames = batch["vae_images"].shape[1]
+        try:
+            import dwm.utils.preview as up
+            tensor = up.make_ctsd_preview_tensor(images, batch, self.inference_config)
+            if frames == 1:
+                torchvision.transforms.functional.to_pil_image(tensor).save(
+                    os.path.join(folder, name + ".png"))
+            else:
+                up.save_tensor_to_video(os.path.join(folder, name + ".mp4"), "libx264",
+                                        batch["fps"][0].item(), tensor)
+        except ImportError:
+            B, _, V = batch["vae_images"].shape[:3]
+            grid = images.float().cpu().unflatten(0, (B, -1, V))
+            for t in range(grid.shape[1]):
+                torchvision.utils.save_image(
+                    grid[:, t].flatten(0, 1), os.path.join(
+                        folder, name + (".png" if grid.shape[1] == 1 else "_%04d.png" % t)),
+                    nrow=V)
+
+    @torch.no_grad()
+    def preview_pipeline(self, batch: dict, output_path: str, global_step: int):
+        """Generates the whole clip of `batch` (autoregressively when
+        `sequence_length_per_iteration` is configured) and dumps it (reference :1836-1897)."""
+        n = batch["vae_images"].shape[1]
+        if "sequence_length_per_iteration" in self.inference_config:
+            shape = self._preview_latent_shape(batch, self.get_latent_sequence_length(
+                self.inference_config["sequence_length_per_iteration"]))
+            out = self.autoregressive_inference_pipeline(shape, batch, "pt")
+        else:
+            shape = self._preview_latent_shape(batch, self.get_latent_sequence_length(n))
+            out = self.inference_pipeline(shape, batch, "pt")
+        self._dump_preview(out["images"], batch, output_path, global_step)
+        return out
+
+
 class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
 
     def reset_streaming(self, latent_shape, output_type):
@@ -860,3 +916,13 @@ class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
         if output_type == "pt":
             result["images"] = torch.cat(result["images"])
         return result
+
+    @torch.no_grad()
+    def preview_pipeline(self, batch: dict, output_path: str, global_step: int):
+        """FIFO generation of the whole clip (reference :2280-2330)."""
+        assert "sequence_length_per_iteration" in self.inference_config
+        shape = self._preview_latent_shape(
+            batch, self.inference_config["sequence_length_per_iteration"])
+        out = self.fifo_inference_pipeline(shape, batch, "pt")
+        self._dump_preview(out["images"], batch, output_path, global_step)
+        return out

@@ -434,3 +434,38 @@ def run_text_case(pipeline_cls, model_classes, name, stack):
                                      text_condition_mask=mask, do_classifier_free_guidance=cfg)
     return {k: tensor_fingerprint(rc[k]) for k in ("encoder_hidden_states", "pooled_projections")
             if rc.get(k) is not None}
+
+
+# -- preview_pipeline: latent-shape derivation and dispatch ----------------------------------------
+
+PREVIEW_CASES = {
+    # name -> (streaming class?, inference_config, frames in the batch, temporal VAE down blocks)
+    "single_window": (False, {"inference_steps": 4}, 5, 4),
+    "autoregressive": (False, {"inference_steps": 4, "sequence_length_per_iteration": 6,
+                               "reference_frame_count": 2}, 14, 4),
+    "temporal_vae": (False, {"inference_steps": 4, "sequence_length_per_iteration": 17,
+                             "vae_pre": 1, "vae_stride": 4}, 33, 4),
+    "streaming": (True, {"inference_steps": 12, "sequence_length_per_iteration": 4}, 9, 3),
+}
+
+
+def run_preview_case(base_cls, streaming_cls, name):
+    streaming, inf, frames, n_down = PREVIEW_CASES[name]
+    pipe = object.__new__(streaming_cls if streaming else base_cls)
+    pipe.inference_config, pipe.common_config, pipe.training_config = inf, {}, {}
+    pipe.should_save = False
+    pipe.vae = type("V", (), {"config": type("C", (), {
+        "down_block_types": ("D",) * n_down, "latent_channels": 16})()})()
+    calls = []
+
+    def rec(kind):
+        def f(latent_shape, batch, output_type):
+            calls.append([kind, list(latent_shape), list(batch["vae_images"].shape), output_type])
+            return {"images": torch.zeros(1)}
+        return f
+    for kind in ("inference_pipeline", "autoregressive_inference_pipeline",
+                 "fifo_inference_pipeline"):
+        setattr(pipe, kind, rec(kind))
+    batch = {"vae_images": torch.zeros(2, frames, 6, 3, 256, 448), "fps": torch.tensor([10.0])}
+    pipe.preview_pipeline(batch, "/nonexistent", 0)
+    return calls

@@ -49,7 +49,7 @@ import torch  # noqa: E402
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON,  # noqa: E402
                     FULL_SEQUENCE_CASES, TINY, VARIANTS, full_sequence_inputs,
                     run_autoregressive_case, run_fifo_case, run_text_case, tiny_text_stack,
-                    TEXT_CASES,
+                    TEXT_CASES, PREVIEW_CASES, run_preview_case,
                     condition_batch, scheduler_inputs, seeded_oracle, synthetic_inputs,
                     variant_case)
 
@@ -231,6 +231,10 @@ def main():
               for name in AUTOREGRESSIVE_CASES}
     # streaming FIFO (ctsd.py:2012-2278): reset_streaming / send_frame_condition /
     # receive_frame / fifo_inference_pipeline with the real streaming-mode get_conditions
+    traces["preview_dispatch"] = {
+        name: run_preview_case(ref_pipe.CrossviewTemporalSD,
+                               ref_pipe.StreamingCrossviewTemporalSD, name)
+        for name in PREVIEW_CASES}
     traces["streaming_fifo"] = run_fifo_case(
         ref_pipe.StreamingCrossviewTemporalSD, object.__new__(diffusers.SD3Transformer2DModel))
 

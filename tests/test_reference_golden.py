@@ -14,7 +14,7 @@ import torch
 from common import (AUTOREGRESSIVE_CASES, CONDITION_CASES, CONDITION_COMMON, FULL_SEQUENCE_CASES,
                     TINY, VARIANTS, full_sequence_inputs,
                     condition_batch, run_autoregressive_case, run_fifo_case, run_text_case,
-                    TEXT_CASES, tiny_text_stack,
+                    TEXT_CASES, tiny_text_stack, PREVIEW_CASES, run_preview_case,
                     scheduler_inputs, seeded_oracle, synthetic_inputs, variant_case)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -248,6 +248,18 @@ def test_mirror_text_conditions_match_reference(name, text_stack):
         for f in ("sum", "weighted", "abs"):
             assert got[k][f] == pytest.approx(want[k][f], rel=1e-6, abs=1e-6), (k, f)
         assert got[k]["samples"] == pytest.approx(want[k]["samples"], rel=1e-5, abs=1e-6)
+
+
+@pytest.mark.parametrize("name", list(PREVIEW_CASES))
+def test_mirror_preview_pipeline_dispatch_matches_reference(name):
+    """`preview_pipeline` (what src/dwm/preview.py calls): latent shape derived from the batch
+    image size / VAE config / temporal-VAE frame arithmetic, and which generation pipeline is
+    run, equal to the reference's for both pipeline classes."""
+    import json
+    from dwm.pipelines.ctsd import CrossviewTemporalSD, StreamingCrossviewTemporalSD
+    with open(os.path.join(HERE, "golden", "reference_autoregressive_traces.json")) as f:
+        want = json.load(f)["preview_dispatch"][name]
+    assert run_preview_case(CrossviewTemporalSD, StreamingCrossviewTemporalSD, name) == want
 
 
 def test_df_index_schedule_matches_reference_loop_arithmetic():
