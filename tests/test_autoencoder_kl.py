@@ -117,11 +117,7 @@ def test_softmax_rows():
         assert abs(out.float().sum(-1) - 1).max().item() < 2e-2
 
 
-# GPU validation pending: written after the round's GPU budget was spent.  Opt in with
-# DWM_RUN_UNVALIDATED=1 (first thing to run next round).
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("DWM_RUN_UNVALIDATED", "0") != "1",
-                    reason="encode path not yet run on a GPU (set DWM_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("name,dtype,tol", [("sd35", torch.float16, 6e-3),
                                             ("sd21", torch.float16, 6e-3)])
 def test_encode_matches_oracle(name, dtype, tol):
