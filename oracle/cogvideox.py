@@ -175,3 +175,126 @@ class AutoencoderKLCogVideoXDecoder(nn.Module):
             y, cache = self.decoder(z[:, :, start:end], cache)
             out.append(y)
         return torch.cat(out, dim=2)
+
+
+# -- encoder (diffusers==0.31.0 CogVideoXEncoder3D, AutoencoderKLCogVideoX._encode; reference use:
+#    src/dwm/pipelines/ctsd.py:1677-1700 when generate_frames_for_reference is false) ---------------
+
+class EncResnetBlock3D(nn.Module):
+    """CogVideoXResnetBlock3D with spatial_norm_dim=None: plain GroupNorm (eps 1e-6)."""
+
+    def __init__(self, in_channels, out_channels, groups=32):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=1e-6)
+        self.conv1 = CausalConv3d(in_channels, out_channels, 3)
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=1e-6)
+        self.conv2 = CausalConv3d(out_channels, out_channels, 3)
+        self.conv_shortcut = nn.Conv3d(in_channels, out_channels, 1) \
+            if in_channels != out_channels else None
+
+    def forward(self, inputs, cache):
+        new_cache = {}
+        h, new_cache["conv1"] = self.conv1(F.silu(self.norm1(inputs)), cache.get("conv1"))
+        h, new_cache["conv2"] = self.conv2(F.silu(self.norm2(h)), cache.get("conv2"))
+        if self.conv_shortcut is not None:
+            inputs = self.conv_shortcut(inputs)
+        return h + inputs, new_cache
+
+
+class Downsample3D(nn.Module):
+    """CogVideoXDownsample3D: optional temporal average pooling in pairs (an odd frame count
+    keeps its first frame), then right / bottom zero pad + stride-2 3x3 conv per frame."""
+
+    def __init__(self, channels, compress_time):
+        super().__init__()
+        self.compress_time = compress_time
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=0)
+
+    def forward(self, x):
+        if self.compress_time:
+            b, c, f, h, w = x.shape
+            x = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, f)
+            if f % 2 == 1:
+                first, rest = x[..., 0], x[..., 1:]
+                if rest.shape[-1] > 0:
+                    rest = F.avg_pool1d(rest, kernel_size=2, stride=2)
+                x = torch.cat([first[..., None], rest], dim=-1)
+            else:
+                x = F.avg_pool1d(x, kernel_size=2, stride=2)
+            x = x.reshape(b, h, w, c, x.shape[-1]).permute(0, 3, 4, 1, 2)
+        x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+        b, c, f, h, w = x.shape
+        x = self.conv(x.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w))
+        return x.reshape(b, f, *x.shape[1:]).permute(0, 2, 1, 3, 4)
+
+
+class _DownBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, num_layers, downsample, compress_time, groups):
+        super().__init__()
+        self.resnets = nn.ModuleList([
+            EncResnetBlock3D(in_channels if i == 0 else out_channels, out_channels, groups)
+            for i in range(num_layers)])
+        self.downsamplers = nn.ModuleList(
+            [Downsample3D(out_channels, compress_time)]) if downsample else None
+
+    def forward(self, h, cache):
+        new_cache = {}
+        for i, r in enumerate(self.resnets):
+            h, new_cache[i] = r(h, cache.get(i, {}))
+        if self.downsamplers is not None:
+            h = self.downsamplers[0](h)
+        return h, new_cache
+
+
+class Encoder3D(nn.Module):
+    def __init__(self, in_channels=3, out_channels=16,
+                 block_out_channels=(128, 256, 256, 512), layers_per_block=3,
+                 norm_num_groups=32, temporal_compression_ratio=4):
+        super().__init__()
+        boc = list(block_out_channels)
+        self.conv_in = CausalConv3d(in_channels, boc[0], 3)
+        level = int(np.log2(temporal_compression_ratio))
+        self.down_blocks = nn.ModuleList()
+        out_ch = boc[0]
+        for i in range(len(boc)):
+            prev, out_ch = out_ch, boc[i]
+            self.down_blocks.append(_DownBlock(prev, out_ch, layers_per_block,
+                                               i != len(boc) - 1, i < level, norm_num_groups))
+        self.mid_block = _DownBlock(boc[-1], boc[-1], 2, False, False, norm_num_groups)
+        self.norm_out = nn.GroupNorm(norm_num_groups, boc[-1], eps=1e-6)
+        self.conv_out = CausalConv3d(boc[-1], 2 * out_channels, 3)
+
+    def forward(self, sample, cache=None):
+        cache = cache or {}
+        new_cache = {}
+        h, new_cache["conv_in"] = self.conv_in(sample, cache.get("conv_in"))
+        for i, blk in enumerate(self.down_blocks):
+            h, new_cache[i] = blk(h, cache.get(i, {}))
+        h, new_cache["mid"] = self.mid_block(h, cache.get("mid", {}))
+        h, new_cache["conv_out"] = self.conv_out(F.silu(self.norm_out(h)), cache.get("conv_out"))
+        return h, new_cache
+
+
+class AutoencoderKLCogVideoXEncoder(nn.Module):
+    """encode(x): chunks of `num_sample_frames_batch_size` (8) frames, the first chunk takes
+    the remainder; causal-conv caches carried across chunks; moments = mean | logvar."""
+
+    def __init__(self, **encoder_kwargs):
+        super().__init__()
+        self.encoder = Encoder3D(**encoder_kwargs)
+        self.num_sample_frames_batch_size = 8
+
+    def encode_moments(self, x):
+        fb = self.num_sample_frames_batch_size
+        n = x.shape[2]
+        cache, out = None, []
+        for i in range(max(n // fb, 1)):
+            rem = n % fb
+            start = fb * i + (0 if i == 0 else rem)
+            end = fb * (i + 1) + rem
+            y, cache = self.encoder(x[:, :, start:end], cache)
+            out.append(y)
+        return torch.cat(out, dim=2)
+
+    def encode_mode(self, x):
+        return torch.chunk(self.encode_moments(x), 2, dim=1)[0]

@@ -81,7 +81,8 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
                  block_out_channels=(128, 256, 256, 512), latent_channels=16,
                  layers_per_block=3, norm_num_groups=32,
                  temporal_compression_ratio=4, scaling_factor=1.15258426,
-                 shift_factor=None, compute_dtype=torch.bfloat16, **unused):
+                 shift_factor=None, compute_dtype=torch.bfloat16, with_encoder=False,
+                 **unused):
         super().__init__()
         self.config = _Cfg(
             in_channels=in_channels, out_channels=out_channels,
@@ -110,6 +111,46 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
         d.conv_out = _causal(rev[-1], out_channels, 3)
         self.decoder = d
         self._pk = None
+        self._pk_enc = None
+        self.num_sample_frames_batch_size = 8
+        if with_encoder:       # opt-in until its GPU parity test has run (tests/test_vae_gpu.py)
+            self.encoder = self._build_encoder(in_channels, latent_channels, block_out_channels,
+                                               layers_per_block, g, level)
+
+    @staticmethod
+    def _build_encoder(in_channels, latent_channels, block_out_channels, layers_per_block, g,
+                       level):
+        def enc_resnet(cin, cout):
+            m = _P()
+            m.norm1 = torch.nn.GroupNorm(g, cin, eps=1e-6)
+            m.conv1 = _causal(cin, cout, 3)
+            m.norm2 = torch.nn.GroupNorm(g, cout, eps=1e-6)
+            m.conv2 = _causal(cout, cout, 3)
+            if cin != cout:
+                m.conv_shortcut = torch.nn.Conv3d(cin, cout, 1)
+            return m
+        boc = list(block_out_channels)
+        e = _P()
+        e.conv_in = _causal(in_channels, boc[0], 3)
+        e.down_blocks = torch.nn.ModuleList()
+        out_ch = boc[0]
+        for i in range(len(boc)):
+            prev, out_ch = out_ch, boc[i]
+            b = _P()
+            b.resnets = torch.nn.ModuleList(
+                [enc_resnet(prev if j == 0 else out_ch, out_ch) for j in range(layers_per_block)])
+            b.compress_time = i < level
+            if i != len(boc) - 1:
+                dn = _P()
+                dn.conv = torch.nn.Conv2d(out_ch, out_ch, 3, stride=2, padding=0)
+                b.downsamplers = torch.nn.ModuleList([dn])
+            e.down_blocks.append(b)
+        e.mid_block = _P()
+        e.mid_block.resnets = torch.nn.ModuleList(
+            [enc_resnet(boc[-1], boc[-1]), enc_resnet(boc[-1], boc[-1])])
+        e.norm_out = torch.nn.GroupNorm(g, boc[-1], eps=1e-6)
+        e.conv_out = _causal(boc[-1], 2 * latent_channels, 3)
+        return e
 
     # -- diffusers-style plumbing -------------------------------------------------------
     @property
@@ -139,11 +180,11 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
         return vae
 
     def _apply(self, fn, *a, **k):
-        self._pk = None
+        self._pk = self._pk_enc = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        self._pk = None
+        self._pk = self._pk_enc = None
         return super().load_state_dict(state_dict, strict=strict, assign=assign)
 
     # -- weight packing --------------------------------------------------------------------
@@ -267,6 +308,153 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
                               epilogue=_lib.EPI_F32)
         n, T, H, W = shape
         return y.view(n, T, H, W, -1)[..., :self.config.out_channels], new_cache
+
+    # -- encoder (opt-in, `with_encoder=True`) ---------------------------------------------------
+    @torch.no_grad()
+    def _pack_encoder(self):
+        e = self.encoder
+        dev = e.conv_in.conv.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("AutoencoderKLCogVideoX.encode runs on CUDA (sm_100a) only; "
+                               "there is no CPU fallback.")
+        dt = self.compute_dtype
+
+        def conv3(conv, pad_in=None, pad_out=None):
+            w = _ops.pack_conv_weight(conv.weight.to(dev), dt, pad_out_to=pad_out,
+                                      pad_in_to=pad_in)
+            b = torch.zeros(w.shape[1], device=dev)
+            b[:conv.out_channels] = conv.bias.detach().float()
+            return w, b
+
+        def gn(n):
+            return (n.weight.detach().float().to(dev).contiguous(),
+                    n.bias.detach().float().to(dev).contiguous())
+
+        def res(m):
+            p = dict(n1=gn(m.norm1), c1=conv3(m.conv1.conv), n2=gn(m.norm2),
+                     c2=conv3(m.conv2.conv))
+            if hasattr(m, "conv_shortcut"):
+                c = m.conv_shortcut
+                p["sc"] = (c.weight.detach().reshape(c.out_channels, -1).to(dev, dt).contiguous(),
+                           c.bias.detach().float().to(dev).contiguous())
+            return p
+        pk = dict(conv_in=conv3(e.conv_in.conv, pad_in=16), downs=[])
+        for blk in e.down_blocks:
+            b = dict(res=[res(r) for r in blk.resnets], compress=blk.compress_time)
+            if hasattr(blk, "downsamplers"):
+                b["down"] = conv3(blk.downsamplers[0].conv)
+            pk["downs"].append(b)
+        pk["mid"] = [res(r) for r in e.mid_block.resnets]
+        pk["norm_out"] = gn(e.norm_out)
+        lc2 = 2 * self.config.latent_channels
+        pk["conv_out"] = conv3(e.conv_out.conv, pad_out=(lc2 + 31) // 32 * 32)
+        self._pk_enc = pk
+        return pk
+
+    def _gn_act(self, h, shape, p, groups):
+        """GroupNorm + SiLU of fp32 `h` [rows, C] -> 16-bit time-padded conv input."""
+        nb, T, H, W = shape
+        C = h.shape[1]
+        h5 = h.view(nb, T, H, W, C)
+        sums = _ops.groupnorm_stats(h5, groups)
+        out = torch.empty(nb, T + 2, H, W, C, device=h.device, dtype=self.compute_dtype)
+        _ops.spatialnorm_silu(h5, sums, p[0], p[1], out, groups=groups, eps=1e-6, out_t0=2,
+                              silu=True)
+        return out
+
+    def _enc_resnet(self, name, h, shape, p, groups, cache, new_cache):
+        a = self._gn_act(h, shape, p["n1"], groups)
+        h1 = self._causal_conv(name + ".conv1", a, p["c1"], cache, new_cache,
+                               epilogue=_lib.EPI_F32)
+        b = self._gn_act(h1, shape, p["n2"], groups)
+        if "sc" in p:
+            h16 = torch.empty(h.shape, device=h.device, dtype=self.compute_dtype)
+            _ops.act_cast(h, h16)
+            skip = _ops.linear(h16, *p["sc"], epilogue=_lib.EPI_F32)
+        else:
+            skip = h
+        return self._causal_conv(name + ".conv2", b, p["c2"], cache, new_cache,
+                                 epilogue=_lib.EPI_RESID, resid=skip)
+
+    def _downsample(self, h, shape, blk):
+        """CogVideoXDownsample3D: pairwise temporal mean (an odd frame count keeps its first
+        frame), then the stride-2 conv with right / bottom padding = the odd positions of a
+        stride-1 'same' convolution."""
+        nb, T, H, W = shape
+        C = h.shape[1]
+        h5 = h.view(nb, T, H, W, C)
+        if blk["compress"] and T > 1:
+            first = h5[:, :1] if T % 2 == 1 else None
+            rest = h5[:, 1:] if T % 2 == 1 else h5
+            pairs = rest.shape[1] // 2
+            a = rest[:, 0:2 * pairs:2].contiguous()
+            b = rest[:, 1:2 * pairs:2].contiguous()
+            half = self.__dict__.get("_half")
+            if half is None or half.device != h.device:
+                half = self._half = torch.full((1,), 0.5, device=h.device)
+            pooled = _ops.lincomb2(a, b, half, half, torch.empty_like(a))
+            h5 = pooled if first is None else torch.cat([first, pooled], 1)
+            T = h5.shape[1]
+        x16 = torch.empty(nb, T, H, W, C, device=h.device, dtype=self.compute_dtype)
+        _ops.act_cast(h5.contiguous(), x16)
+        y = _ops.conv(x16, *blk["down"], kernel=(1, 3, 3), epilogue=_lib.EPI_F32)
+        y = y.view(nb, T, H, W, C)[:, :, 1::2, 1::2].contiguous()
+        return y.view(-1, C), (nb, T, H // 2, W // 2)
+
+    def _encode_chunk(self, x, cache):
+        """x: fp32 channels-last frames [nb, T, H, W, 3] -> moments rows, shape, new cache."""
+        pk, dt = self._pk_enc, self.compute_dtype
+        groups = self.config.norm_num_groups
+        nb, T, H, W, cin = x.shape
+        new_cache = {}
+        cp = pk["conv_in"][0].shape[2]
+        xin = torch.zeros(nb, T + 2, H, W, cp, device=x.device, dtype=dt)
+        xin[:, 2:, ..., :cin] = x
+        h = self._causal_conv("enc.conv_in", xin, pk["conv_in"], cache, new_cache,
+                              epilogue=_lib.EPI_F32)
+        shape = (nb, T, H, W)
+        for bi, blk in enumerate(pk["downs"]):
+            for ri, p in enumerate(blk["res"]):
+                h = self._enc_resnet("enc.down%d.%d" % (bi, ri), h, shape, p, groups, cache,
+                                     new_cache)
+            if "down" in blk:
+                h, shape = self._downsample(h, shape, blk)
+        for ri, p in enumerate(pk["mid"]):
+            h = self._enc_resnet("enc.mid.%d" % ri, h, shape, p, groups, cache, new_cache)
+        a = self._gn_act(h, shape, pk["norm_out"], groups)
+        y = self._causal_conv("enc.conv_out", a, pk["conv_out"], cache, new_cache,
+                              epilogue=_lib.EPI_F32)
+        n, T, H, W = shape
+        return y.view(n, T, H, W, -1)[..., :2 * self.config.latent_channels], new_cache
+
+    @torch.no_grad()
+    def encode(self, x, return_dict: bool = True):
+        """x: [B, 3, T, H, W] frames in [-1, 1] -> `.latent_dist` (mode / sample), frames
+        processed in chunks of 8 (the first chunk takes the remainder) with the causal-conv
+        caches carried across chunks (diffusers 0.31 `_encode`; reference ctsd.py:1677-1700)."""
+        if not hasattr(self, "encoder"):
+            raise NotImplementedError("construct AutoencoderKLCogVideoX(with_encoder=True)")
+        if not x.is_cuda:
+            raise RuntimeError("AutoencoderKLCogVideoX.encode needs CUDA tensors; there is no "
+                               "CPU fallback.")
+        if self._pk_enc is None:
+            self._pack_encoder()
+        from dwm.models.autoencoder_kl import DiagonalGaussianDistribution
+        xcl = x.float().permute(0, 2, 3, 4, 1).contiguous()
+        fb = self.num_sample_frames_batch_size
+        n = xcl.shape[1]
+        cache, outs = {}, []
+        for i in range(max(n // fb, 1)):
+            rem = n % fb
+            start = fb * i + (0 if i == 0 else rem)
+            end = fb * (i + 1) + rem
+            y, cache = self._encode_chunk(xcl[:, start:end].contiguous(), cache)
+            outs.append(y)
+        moments = torch.cat(outs, dim=1).permute(0, 4, 1, 2, 3).contiguous().to(x.dtype)
+        dist = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (dist,)
+        return _Cfg(latent_dist=dist)
 
     # -- public API ------------------------------------------------------------------------------
     @torch.no_grad()

@@ -650,12 +650,17 @@ class CrossviewTemporalSD:
         if not inf.get("generate_frames_for_reference", True):
             # reference frames from real images: VAE-encode batch["vae_images"] (reference
             # :1677-1700).  Image VAEs only; the temporal-VAE encoder is not mirrored.
-            if self.is_temporal_vae or not hasattr(self.vae, "encode"):
+            if not hasattr(self.vae, "encode") or \
+                    (self.is_temporal_vae and not hasattr(self.vae, "encoder")):
                 raise NotImplementedError(
-                    "reference frames from batch[\"vae_images\"] need a VAE encoder; only the "
-                    "2-D AutoencoderKL encoder is provided (SURVEY.md §8(f)3)")
+                    "reference frames from batch[\"vae_images\"] need a VAE encoder: "
+                    "AutoencoderKL has one, AutoencoderKLCogVideoX only when built with "
+                    "with_encoder=True (SURVEY.md §8(f)3)")
             raw = batch["vae_images"][:, :n_ref]
             x = raw.flatten(0, 2).to(self.device) * 2 - 1        # VaeImageProcessor.preprocess
+            Bi, Ti, Vi = raw.shape[:3]
+            if self.is_temporal_vae:      # "(b t v) c h w -> (b v) c t h w"
+                x = x.unflatten(0, (Bi, Ti, Vi)).permute(0, 2, 3, 1, 4, 5).flatten(0, 1)
             shift = self.vae.config.shift_factor \
                 if self.vae.config.shift_factor is not None else 0
             enc = dwm.functional.memory_efficient_split_call(
@@ -663,7 +668,10 @@ class CrossviewTemporalSD:
                 lambda block, t: (block.encode(t).latent_dist.mode() - shift) *
                 block.config.scaling_factor,
                 self.common_config.get("memory_efficient_batch", -1))
-            image_latents = enc.unflatten(0, raw.shape[:3])
+            if self.is_temporal_vae:      # "(b v) c t h w -> b t v c h w"
+                image_latents = enc.unflatten(0, (Bi, Vi)).permute(0, 3, 1, 2, 4, 5)
+            else:
+                image_latents = enc.unflatten(0, raw.shape[:3])
         images = []
         stride = win - n_ref
         starts = range(0, n_total - win + 1, stride)

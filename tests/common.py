@@ -196,6 +196,11 @@ AUTOREGRESSIVE_CASES = {
                                    "reference_frame_count": 2,
                                    "generate_frames_for_reference": False},
                                   (1, 6, 3, 4, 2, 3), 14, False),
+    "temporal_vae_encoded_reference": ({"frame_prediction_style": "ctsd"},
+                                       {"inference_steps": 8, "sequence_length_per_iteration": 17,
+                                        "reference_frame_count": 1, "vae_pre": 1, "vae_stride": 4,
+                                        "generate_frames_for_reference": False},
+                                       (1, 5, 3, 4, 2, 3), 33, True),
     "diffusion_forcing": ({"frame_prediction_style": "diffusion_forcing"},
                           {"inference_steps": 12, "sequence_length_per_iteration": 4,
                            "autoregression_data_exception_for_take_sequence":
@@ -218,7 +223,7 @@ class _TraceVae:
 
     @staticmethod
     def encode(x):
-        z = torch.cat([x, x[:, :1]], 1)[:, :, ::8, ::8]
+        z = torch.cat([x, x[:, :1]], 1)[..., ::8, ::8]      # image [n,c,h,w] or clip [n,c,t,h,w]
         dist = type("D", (), {"mode": lambda self: z})()
         return type("O", (), {"latent_dist": dist})()
 
@@ -270,6 +275,7 @@ def run_autoregressive_case(cls, name):
     pipe.is_temporal_vae = temporal
     pipe.test_scheduler = type("S", (), {"init_noise_sigma": 1.0})()
     pipe.vae = _TraceVae()
+    pipe.vae.encoder = None            # marks "has an encoder" for the temporal-VAE branch
     pipe.image_processor = type("P", (), {"preprocess": staticmethod(lambda t: 2.0 * t - 1.0)})()
     trace = []
     install_fake_inference_pipeline(pipe, trace)

@@ -53,3 +53,67 @@ def test_decode_matches_oracle(frames, dtype, tol):
     assert y.shape == ref.shape and y.shape[0] == 2 and y.shape[-2:] == (32, 56)
     err = ((y.float() - ref).abs().max() / ref.abs().max()).item()
     assert err < tol, err
+
+
+# -- encoder (opt-in `with_encoder=True`) ---------------------------------------------------------
+
+def _enc_pair(dtype):
+    from oracle import cogvideox as oc
+    from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
+    torch.manual_seed(0)
+    o = oc.AutoencoderKLCogVideoXEncoder(**CFG)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for n, p in o.named_parameters():
+            if p.dim() == 1 and n.endswith(".weight"):
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+            elif p.dim() == 1:
+                p.copy_(0.05 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(torch.randn(p.shape, generator=g) * (1.5 / p[0].numel()) ** 0.5)
+    m = AutoencoderKLCogVideoX(**CFG, compute_dtype=dtype, with_encoder=True)
+    return o, m
+
+
+def test_encoder_state_dict_keys_cpu():
+    from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
+    o, m = _enc_pair(torch.bfloat16)
+    plain = AutoencoderKLCogVideoX(**CFG)
+    assert not any(k.startswith("encoder.") for k in plain.state_dict())     # default unchanged
+    so = o.state_dict()
+    sm = {k: v for k, v in m.state_dict().items() if k.startswith("encoder.")}
+    assert set(so) == set(sm)
+    for k in so:
+        assert so[k].shape == sm[k].shape, k
+    m.load_state_dict({**plain.state_dict(), **so}, strict=True)
+    with pytest.raises(NotImplementedError):
+        plain.encode(torch.zeros(1, 3, 1, 32, 48))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.encode(torch.zeros(1, 3, 1, 32, 48))
+    # frame arithmetic of the oracle: 1 -> 1, 9 -> 3, 17 -> 5 latent frames
+    with torch.no_grad():
+        for t, tz in ((1, 1), (9, 3), (17, 5)):
+            assert o.encode_mode(torch.zeros(1, 3, t, 16, 16)).shape == (1, 16, tz, 2, 2)
+
+
+# Written after the round's GPU budget was spent: first thing to run next round
+# (DWM_RUN_UNVALIDATED=1 python -m pytest tests/test_vae_gpu.py -m gpu -k encode).
+@pytest.mark.gpu
+@pytest.mark.skipif(__import__("os").environ.get("DWM_RUN_UNVALIDATED", "0") != "1",
+                    reason="CogVideoX encoder not yet run on a GPU (set DWM_RUN_UNVALIDATED=1)")
+@pytest.mark.parametrize("frames", [1, 9, 17])
+def test_encode_matches_oracle(frames):
+    o, m = _enc_pair(torch.float16)
+    o = o.cuda()
+    sd = dict(m.state_dict())
+    sd.update(o.state_dict())
+    m.load_state_dict(sd)
+    m.cuda()
+    g = torch.Generator().manual_seed(frames)
+    x = (torch.rand(2, 3, frames, 32, 48, generator=g) * 2 - 1).cuda().half()
+    with torch.no_grad():
+        ref = o.encode_moments(x.float())
+    d = m.encode(x).latent_dist
+    assert d.parameters.shape == ref.shape
+    err = ((d.parameters.float() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 8e-3, err
