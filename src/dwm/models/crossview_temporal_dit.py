@@ -412,6 +412,14 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                self._tkey(crossview_attention_mask))
         if key == self._cond_key:
             return self._cond
+        if self.__dict__.pop("_ring_shift", False) and self._ring_applicable(
+                B, T, V, Hp, Wp, t_offset, T_total, condition_image_tensor):
+            cd = self._conditions_shifted(
+                B, T, V, Hp, Wp, encoder_hidden_states, pooled_projections,
+                condition_image_tensor, added_time_ids, disable_crossview, disable_temporal,
+                crossview_attention_mask)
+            self._cond_key, self._cond = key, cd
+            return cd
         pk, dt, D = self._pk, self._pk["dtype"], self.inner_dim
         dev = encoder_hidden_states.device
         N, S = B * T * V, Hp * Wp
@@ -444,8 +452,10 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
             .expand(B, T, V).reshape(-1)
         item_v = torch.arange(V, device=dev).view(1, 1, V)\
             .expand(B, T, V).reshape(-1)
+        cd["_geom"], cd["_view_cam"] = (B, T, V, Hp, Wp, t_offset, T_total), view_cam
         if self.enable_temporal:
             tabs = index_table(T_total, pk["tpe"])
+            cd["_tabs_t"] = tabs
             cd["temb_tab"] = []
             for tab in tabs:
                 e = tab[item_t]
@@ -459,6 +469,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                              for m in self.time_mixers]
         if self.enable_crossview:
             tabs = index_table(V, pk["vpe"])
+            cd["_tabs_v"] = tabs
             cd["vemb_tab"] = []
             for tab in tabs:
                 e = tab[item_v]
@@ -478,6 +489,61 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
             cd["residuals"] = self.condition_image_adapter.token_features(
                 condition_image_tensor.to(dev), dt)
         self._cond_key, self._cond = key, cd
+        return cd
+
+    # -- streaming ring update of the step-invariant cache (opt-in) -----------
+    def _ring_applicable(self, B, T, V, Hp, Wp, t_offset, T_total, image):
+        old = self._cond
+        return old is not None and T > 1 and t_offset == 0 and T_total == T and \
+            old.get("_geom") == (B, T, V, Hp, Wp, 0, T) and \
+            (image is None or image.shape[1] == T)
+
+    def _conditions_shifted(self, B, T, V, Hp, Wp, ehs, pooled, image, ids, dis_cv, dis_t, mask):
+        """The FIFO moved on by one frame: every per-item entry of the cached condition set is
+        the old one shifted by a frame, only the last frame's entries (context embedding, pooled
+        text MLP, camera embedding, ImageAdapter residuals) are computed.  The index-embedding
+        sums are re-formed because a frame's time index changes with its queue slot."""
+        old = self._cond
+        saved = (self._cond_key, self._cond)
+        self._cond_key = None
+        one = lambda t: None if t is None else t[:, T - 1:]          # noqa: E731
+        cd1 = self._conditions(B, 1, V, Hp, Wp, T - 1, T, one(ehs), one(pooled), one(image),
+                               one(ids), dis_cv, dis_t, mask)
+        self._cond_key, self._cond = saved
+
+        def shift(o, n):
+            if o is None:
+                return None
+            rows = o.shape[0] // (B * T)            # rows per (batch, frame): V * rows per item
+            o4 = o.view(B, T, rows, o.shape[1])
+            return torch.cat([o4[:, 1:], n.view(B, 1, rows, o.shape[1])], 1)\
+                .reshape(o.shape).contiguous()
+        cd = dict(old)
+        cd["c0"] = shift(old["c0"], cd1["c0"])
+        cd["text_emb"] = shift(old["text_emb"], cd1["text_emb"])
+        view_cam = cd["_view_cam"] = shift(old["_view_cam"], cd1["_view_cam"])
+        dev = cd["c0"].device
+        item_t = torch.arange(T, device=dev).view(1, T, 1).expand(B, T, V).reshape(-1)
+        item_v = torch.arange(V, device=dev).view(1, 1, V).expand(B, T, V).reshape(-1)
+        if self.enable_temporal:
+            cd["temb_tab"] = []
+            for tab in old["_tabs_t"]:
+                e = tab[item_t]
+                if self.enable_crossview and view_cam is not None and \
+                        not self.disable_view_emb_on_temporal_module:
+                    e = e + view_cam
+                cd["temb_tab"].append(e.contiguous())
+            cd["t_alpha"] = cd1["t_alpha"]
+        if self.enable_crossview:
+            cd["vemb_tab"] = []
+            for tab in old["_tabs_v"]:
+                e = tab[item_v]
+                if view_cam is not None:
+                    e = e + view_cam
+                cd["vemb_tab"].append(e.contiguous())
+            cd["v_alpha"] = cd1["v_alpha"]
+            cd["mask"] = cd1["mask"]
+        cd["residuals"] = [shift(o, n) for o, n in zip(old["residuals"], cd1["residuals"])]
         return cd
 
     # -- attention regroupings (crossview_temporal_dit.py:289-315, 335-361) -----------------

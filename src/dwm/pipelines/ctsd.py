@@ -884,6 +884,11 @@ class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
                 else:
                     self.conditions[k] = torch.cat(
                         [self.conditions[k][:, 1:], v], dim=1)
+            # opt-in: tell the model that the new condition set is the previous one moved on
+            # by a frame, so that it updates its step-invariant cache incrementally
+            if self.inference_config.get(
+                    "condition_ring", os.environ.get("DWM_STREAM_RING", "0") == "1"):
+                self.model._ring_shift = True
             self.latents = torch.cat([
                 self.latents[:, 1:],
                 torch.randn((self.latent_shape[0], 1) + self.latent_shape[2:],
