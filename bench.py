@@ -441,7 +441,6 @@ def cpu_baseline(budget_s=20.0):
     JointTransformerBlock + one VTSelfAttentionBlock at north-star width on a bounded
     number of view-frame items; steps/s extrapolated by FLOPs (all cost is per item)."""
     from oracle import d31, ctsd as octsd
-    from tools import flops as fl
     cores = _host_cores()
     torch.set_num_threads(cores)
     D, S, L, items = 1536, 448, 154, 2

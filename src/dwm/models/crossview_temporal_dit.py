@@ -21,7 +21,6 @@ sequence of `opendwm_b200` kernel launches over pre-packed 16-bit weights:
 With `shard=(rank, world, group)` the frame axis T is sharded across GPUs: cross-view
 blocks stay local, temporal blocks all-gather the post-norm K,V of their frames.
 """
-import math
 from typing import Optional
 
 import torch

@@ -14,7 +14,6 @@ diffusers-side arithmetic underneath stays the unpinned restatement.
 """
 from types import SimpleNamespace
 
-import torch
 from torch import nn
 
 from oracle import d31

@@ -1,7 +1,5 @@
 """Parity of the gathered attention kernel against fp32 softmax(QK^T)V on the same
 16-bit q|k|v, for every regrouping the CTSD DiT uses."""
-import itertools
-
 import pytest
 import torch
 

@@ -3,7 +3,6 @@ restatement, checkpoint round trip through from_pretrained, deprecated attention
 and (GPU) decode parity for SD-3.5-style (16 latent channels, no post_quant_conv) and
 SD-2.1-style (4 latent channels + post_quant_conv) configurations."""
 import json
-import os
 
 import pytest
 import torch
