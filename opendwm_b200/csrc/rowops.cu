@@ -314,7 +314,7 @@ __global__ void patchify_kernel(const float* __restrict__ x, long long items, in
 // ------------------------------------------------------------------ CFG + Euler
 __global__ void cfg_euler_kernel(const float* __restrict__ tok, long long ld_tok, int cfg, float gs,
                                  long long B, long long T, long long V, int C, int H, int W, int P,
-                                 const int* __restrict__ idx, const float* __restrict__ sigmas,
+                                 const int* __restrict__ idx, const float* __restrict__ sigmas, int n_sigmas,
                                  const unsigned char* __restrict__ in_range,
                                  float* __restrict__ lat, float* __restrict__ npred, int round_dtype) {
   const long long total = B * T * V * C * H * W;
@@ -337,6 +337,7 @@ __global__ void cfg_euler_kernel(const float* __restrict__ tok, long long ld_tok
   }
   if (npred) npred[i] = v;
   const int k = idx[btv];
+  if (k < 0 || k + 1 >= n_sigmas) __trap();   // index outside the scheduler table: fail loudly
   const float dsig = sigmas[k + 1] - sigmas[k];
   const float old = lat[i];
   float nv = old + dsig * v;
@@ -349,10 +350,11 @@ __global__ void cfg_euler_kernel(const float* __restrict__ tok, long long ld_tok
 //   x[e] = round(x[e] + (sigma[idx[e / inner] + 1] - sigma[idx[e / inner]]) * v[e])
 __global__ void euler_idx_kernel(const float* __restrict__ v, float* __restrict__ x, long long n,
                                  long long inner, const int* __restrict__ idx,
-                                 const float* __restrict__ sigmas, int round_dtype) {
+                                 const float* __restrict__ sigmas, int n_sigmas, int round_dtype) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int k = idx[i / inner];
+  if (k < 0 || k + 1 >= n_sigmas) __trap();
   float nv = x[i] + (sigmas[k + 1] - sigmas[k]) * v[i];
   if (round_dtype == DWM_BF16) nv = __bfloat162float(__float2bfloat16_rn(nv));
   else if (round_dtype == DWM_F16) nv = __half2float(__float2half_rn(nv));
@@ -409,7 +411,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 //   ts: int32 [B, T, V] current timesteps; prev = ts - step_ratio; alphas: fp32 [num_train]
 __global__ void cfg_ddim_kernel(const float* __restrict__ pred, int cfg, float gs, long long per_b,
                                 long long inner, long long total, const int* __restrict__ ts, int step_ratio,
-                                const float* __restrict__ alphas, float final_alpha, int pred_type,
+                                const float* __restrict__ alphas, int n_alphas, float final_alpha, int pred_type,
                                 float* __restrict__ lat, int round_dtype) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -420,6 +422,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ pred, int cfg, float g
   }
   const int t = ts[i / inner];
   const int tp = t - step_ratio;
+  if (t < 0 || t >= n_alphas || tp >= n_alphas) __trap();   // timestep outside alphas_cumprod
   const float a_t = alphas[t];
   const float a_p = tp >= 0 ? alphas[tp] : final_alpha;
   const float b_t = 1.0f - a_t;
@@ -501,7 +504,7 @@ extern "C" int dwm_b200_cfg_ddim_step(const float* pred, int cfg, float guidance
   const long long total = n_items * inner;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   cfg_ddim_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      pred, cfg, guidance_scale, 0, inner, total, timesteps, step_ratio, alphas_cumprod, final_alpha_cumprod,
+      pred, cfg, guidance_scale, 0, inner, total, timesteps, step_ratio, alphas_cumprod, n_alphas, final_alpha_cumprod,
       prediction_type, latents, round_dtype);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -514,7 +517,7 @@ extern "C" int dwm_b200_euler_step_by_indices(const float* model_output, float* 
               "dwm_b200_euler_step_by_indices: bad arguments");
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
   euler_idx_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(model_output, sample, n, inner, idx,
-                                                                            sigmas, round_dtype);
+                                                                            sigmas, n_sigmas, round_dtype);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -594,7 +597,7 @@ extern "C" int dwm_b200_cfg_euler_step(const float* tokens, int64_t ld_tok, int 
   const long long total = B * T * V * C * H * W;
   const unsigned grid = static_cast<unsigned>((total + 255) / 256);
   cfg_euler_kernel<<<grid, 256, 0, s>>>(tokens, ld_tok, cfg, guidance_scale, B, T, V, C, H, W, patch, idx,
-                                        sigmas, in_range, latents, noise_pred, round_dtype);
+                                        sigmas, n_sigmas, in_range, latents, noise_pred, round_dtype);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

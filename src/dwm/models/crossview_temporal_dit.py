@@ -411,13 +411,17 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                self._tkey(crossview_attention_mask))
         if key == self._cond_key:
             return self._cond
+        # the key holds addresses: keep the keyed tensors alive with the cache entry, so the
+        # caching allocator cannot hand the same address to a different condition set
+        refs = (encoder_hidden_states, pooled_projections, condition_image_tensor,
+                added_time_ids, disable_crossview, disable_temporal, crossview_attention_mask)
         if self.__dict__.pop("_ring_shift", False) and self._ring_applicable(
                 B, T, V, Hp, Wp, t_offset, T_total, condition_image_tensor):
             cd = self._conditions_shifted(
                 B, T, V, Hp, Wp, encoder_hidden_states, pooled_projections,
                 condition_image_tensor, added_time_ids, disable_crossview, disable_temporal,
                 crossview_attention_mask)
-            self._cond_key, self._cond = key, cd
+            self._cond_key, self._cond, self._cond_refs = key, cd, refs
             return cd
         pk, dt, D = self._pk, self._pk["dtype"], self.inner_dim
         dev = encoder_hidden_states.device
@@ -487,7 +491,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
                 condition_image_tensor is not None:
             cd["residuals"] = self.condition_image_adapter.token_features(
                 condition_image_tensor.to(dev), dt)
-        self._cond_key, self._cond = key, cd
+        self._cond_key, self._cond, self._cond_refs = key, cd, refs
         return cd
 
     # -- streaming ring update of the step-invariant cache (opt-in) -----------

@@ -570,6 +570,9 @@ class UNetCrossviewTemporalConditionModel(_compat.UNetSpatioTemporalConditionMod
             disable_temporal, mask))
         if key == self._cond_key:
             return self._cond
+        # keep the keyed tensors alive so their addresses cannot be recycled under the key
+        self._cond_refs = (encoder_hidden_states, condition_image_tensor, added_time_ids,
+                           disable_crossview, disable_temporal, mask)
         B, T, V = geo
         pk, dt = self._pk, self._pk["dtype"]
         dev = encoder_hidden_states.device

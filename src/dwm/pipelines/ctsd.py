@@ -334,6 +334,25 @@ class CrossviewTemporalSD:
         # a slice of the frames and `denoise_step` works on the local latents
         self.sharding = None
 
+    @property
+    def sharding(self):
+        return self._sharding
+
+    @sharding.setter
+    def sharding(self, plan):
+        """Every rank of a sharded window must draw the same noise.  With `generator_seed`
+        configured that holds by construction; otherwise rank 0's seed is broadcast when the
+        plan is attached (the reference is single-process and has no such concern)."""
+        self._sharding = plan
+        if plan is not None and plan.world > 1 and "generator_seed" not in self.config:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError("a ShardPlan with world > 1 needs torch.distributed, or "
+                                   "`generator_seed` in the pipeline config")
+            box = [self.generator.initial_seed()]
+            dist.broadcast_object_list(box, src=0)
+            self.generator.manual_seed(box[0])
+
     # -- the fused denoising step ----------------------------------------------------------
     def _df_step_tensors(self, i, T, spi, take_time, B, V):
         """Device-resident index tensors of one diffusion-forcing step, cached per
@@ -414,8 +433,8 @@ class CrossviewTemporalSD:
         if sharded or stateful:
             return self.denoise_step(latents, conditions, idx, timesteps, in_range)
         key = (latents.data_ptr(), tuple(latents.shape), idx is None, in_range is None,
-               tuple(sorted((k, v.data_ptr()) for k, v in conditions.items()
-                            if torch.is_tensor(v))))
+               tuple(sorted((k, v.data_ptr(), tuple(v.shape), v._version)
+                            for k, v in conditions.items() if torch.is_tensor(v))))
         graphs = self.__dict__.setdefault("_graphs", {})
         g = graphs.get(key)
         if g is None:
@@ -431,8 +450,9 @@ class CrossviewTemporalSD:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.denoise_step(latents, conditions, st["idx"], st["ts"], st["rng"])
-            g = graphs[key] = (graph, st)
-        graph, st = g
+            # the entry keeps the keyed tensors alive (addresses are part of the key)
+            g = graphs[key] = (graph, st, (latents, dict(conditions)))
+        graph, st = g[:2]
         if idx is not None:
             st["idx"].copy_(idx)
         st["ts"].copy_(timesteps)
@@ -585,7 +605,9 @@ class CrossviewTemporalSD:
             if self.is_temporal_vae and self.vae is not None:
                 cur = torch.cat([cur[:, :, None], cur[:, :, None] * 0], dim=2)
                 image_tensor = decode(cur).chunk(2, dim=2)[0]
-                image_tensor = image_tensor.permute(0, 2, 1, 3, 4).flatten(0, 1)
+                # "(b v) c t h w -> (b t v) c h w" (reference :1619-1621)
+                image_tensor = image_tensor.unflatten(0, (B, V))\
+                    .permute(0, 3, 1, 2, 4, 5).flatten(0, 2)
             else:
                 image_tensor = decode(cur)
         else:
@@ -821,8 +843,12 @@ class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
                 i, T, spi, take_time, B, V)
             self.denoise_step(latents, self.conditions, idx, timesteps, in_range)
         if stop_timestep >= steps:
-            self.frames.append(self.decode_latents(
-                latents[:, take_time].flatten(0, 1)))
+            # reference :2092-2101: VAE decode of the exiting frame, then
+            # image_processor.postprocess(image_tensor, self.output_type)
+            image_tensor = self.decode_latents(latents[:, take_time].flatten(0, 1))
+            self.frames.append(
+                image_tensor if self.vae is None else
+                CrossviewTemporalSD.postprocess(image_tensor, self.output_type))
         return latents
 
     @torch.no_grad()

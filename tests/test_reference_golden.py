@@ -316,6 +316,50 @@ def test_cuda_df_loop_matches_reference_loop(golden):
     assert _rel(lat.cpu(), golden["pipe_df_latents_steps_9_10_11"]) < 4e-3
 
 
+class _IdentityVae:
+    """decode = identity, as in tests/golden/make_reference_golden.py: the loop's VAE call
+    site and its post-processing run."""
+    class config:
+        scaling_factor, shift_factor = 1.0, None
+    dtype = torch.float32
+
+    @staticmethod
+    def decode(x, return_dict=False):
+        return (x,)
+
+
+@pytest.mark.gpu
+def test_cuda_streaming_loop_emits_reference_frame(golden):
+    """The mirror's REAL StreamingCrossviewTemporalSD.inference_pipeline (steps 9..11, identity
+    VAE) against what the reference's own loop produced: the returned latents and the frame it
+    appended to `frames` — i.e. VAE call site + image_processor.postprocess (reference
+    ctsd.py:2092-2101), values in [0, 1]."""
+    from dwm.models.crossview_temporal_dit import DiTCrossviewTemporalConditionModel
+    from dwm.pipelines.ctsd import StreamingCrossviewTemporalSD
+    o = seeded_oracle(TINY)
+    m = DiTCrossviewTemporalConditionModel(**TINY, compute_dtype=torch.float16)
+    m.load_state_dict(o.state_dict())
+    pipe = StreamingCrossviewTemporalSD(
+        None, {"generator_seed": 0}, "cuda",
+        {"frame_prediction_style": "diffusion_forcing", "vae_instance": _IdentityVae()},
+        {}, {"guidance_scale": 2.0, "inference_steps": 12, "sequence_length_per_iteration": 4},
+        None, m, model_dtype=torch.float32)
+    sample, _, cond = synthetic_inputs(TINY, device="cuda")
+    shape = (1, 4, 3, 16, 8, 12)
+    pipe.reset_streaming(shape, "pt")
+    pipe.conditions, pipe.latents = cond, sample[:1].clone().float()
+    lat = pipe.inference_pipeline(shape, start_timestep=9, stop_timestep=12)
+    assert _rel(lat.cpu(), golden["pipe_df_latents_steps_9_10_11"]) < 4e-3
+    assert len(pipe.frames) == 1
+    frame, want = pipe.frames[0].cpu(), golden["pipe_df_frame"]
+    assert frame.shape == want.shape
+    assert frame.min().item() >= 0.0 and frame.max().item() <= 1.0
+    assert (frame - want).abs().max().item() < 4e-3        # post-processed range is [0, 1]
+    # and the golden itself is NOT the raw latent frame (the test would be vacuous otherwise)
+    raw = golden["pipe_df_latents_steps_9_10_11"][:, 0].flatten(0, 1)
+    assert (raw - want).abs().max().item() > 0.1
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(FULL_SEQUENCE_CASES))
 def test_cuda_full_sequence_pipeline_matches_reference(name, golden):
