@@ -307,10 +307,20 @@ def run_native(args):
         a[2] += p_["flops"]
     dom_key, dom = max(by_shape.items(), key=lambda kv: kv[1][1])
     achieved = dom[2] / (dom[1] * 1e-3) / 1e12
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_gemm2_geglu_summary.txt: dram read 469.8 MB + write 1035.0 MB)
-    NCU_TRAFFIC = {((86016, 12288, 1536), 1): 469.818368e6 + 1034.998e6}
-    traffic = NCU_TRAFFIC.get(dom_key)
+    # DRAM bytes per launch of that kernel: NOT measurable inside this run (no counters without
+    # ncu); looked up in profiles/ncu_traffic.json, which records, per (M,N,K,epilogue,dtype),
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch and the
+    # capture file it came from.  null when no capture of this kernel shape is committed.
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            for row in json.load(f)["kernels"]:
+                if tuple(row["shape"]) == dom_key[0] and row["epilogue"] == dom_key[1] and \
+                        row.get("dtype", args.dtype) == args.dtype:
+                    traffic = row["dram_read_bytes"] + row["dram_write_bytes"]
+                    traffic_src = row["capture"]
+    except Exception:  # noqa: BLE001
+        pass
     scale = 1.0 if not args.small else None
     line = {
         "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
@@ -330,6 +340,7 @@ def run_native(args):
         "roofline": {
             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+            "traffic_source": traffic_src,
             "kernel": "gemm2_tcgen05_kernel M=%d N=%d K=%d epilogue=%d (CUDA events around "
                       "each of its %d launches in the timed steps)" % (dom_key[0] + (dom_key[1], dom[0])),
             "algorithmic_flops_per_launch": dom[2] / dom[0],
@@ -370,8 +381,40 @@ def run_native(args):
         with open(args.profile_dump, "w") as f:
             json.dump({"ms_per_step": ms, "gemm_ms_per_step": gemm_ms / args.steps,
                        "rows": rows}, f, indent=1)
+    if world == 1 and not args.small and not args.no_extras:
+        # what a user of the reference API sees + the other BASELINE configs + the eager bar;
+        # every piece is wrapped so that a failure never loses the headline
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extras as bx
+        try:
+            line["streaming_e2e"] = bx.streaming_e2e(model, cfg, dev, dtype)
+        except Exception as e:  # noqa: BLE001
+            line["streaming_e2e"] = {"error": repr(e)[:300]}
+        del pipe, model, cond, latents
+        bx._free()
+        line["workloads"] = bx.workloads(dev, dtype)
+        try:
+            line["eager_gpu_baseline"] = bx.eager_gpu_baseline(cfg, dev, dtype)
+            line["eager_gpu_baseline"]["native_speedup"] = \
+                line["eager_gpu_baseline"]["ms_per_step"] / ms
+        except Exception as e:  # noqa: BLE001
+            line["eager_gpu_baseline"] = {"error": repr(e)[:300]}
+        other = "bf16" if args.dtype == "fp16" else "fp16"
+        try:    # same step at the other 16-bit operand type, fresh process (own memory)
+            out = subprocess.run(
+                [sys.executable, os.path.abspath(__file__), "--dtype", other, "--no-extras",
+                 "--no-cpu-baseline", "--steps", str(args.steps), "--warmup",
+                 str(args.warmup)], capture_output=True, text=True, timeout=600)
+            o = json.loads(out.stdout.strip().splitlines()[-1])
+            line["other_dtype"] = {"dtype": other, "value": o["value"], "unit": o["unit"],
+                                   "ms_per_step": o["ms_per_step"],
+                                   "e2e_value": o["e2e"]["value"],
+                                   "roofline_frac": o["roofline"]["frac"],
+                                   "clocks": o.get("clocks")}
+        except Exception as e:  # noqa: BLE001
+            line["other_dtype"] = {"dtype": other, "error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget)
+        line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget, small=args.small)
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -436,52 +479,17 @@ def _host_cores():
     return max(1, min(n, 64))
 
 
-def cpu_baseline(budget_s=20.0):
-    """Oracle (fp32 restatement of the reference) on the host cores: one dual
-    JointTransformerBlock + one VTSelfAttentionBlock at north-star width on a bounded
-    number of view-frame items; steps/s extrapolated by FLOPs (all cost is per item)."""
-    from oracle import d31, ctsd as octsd
-    cores = _host_cores()
-    torch.set_num_threads(cores)
-    D, S, L, items = 1536, 448, 154, 2
-    torch.manual_seed(0)
-    jb = d31.JointTransformerBlock(D, 24, 64, False, "rms_norm", True).eval()
-    vt = octsd.VTSelfAttentionBlock(D, D, 24, 64, "rms_norm").eval()
-    x, c, temb = torch.randn(items, S, D), torch.randn(items, L, D), torch.randn(items, D)
-    xv = torch.randn(items * S // 16, 16, D)
-    f_j = items * ((24 + 8) * S * D * D + 24 * L * D * D + 4 * (S + L) ** 2 * D +
-                   4 * S * S * D + 2 * D * 15 * D)
-    f_v = items * (56 * S * D * D + 4 * 16 * D * S)
-    t_used, reps = 0.0, 0
-    with torch.no_grad():
-        jb(x, c, temb)
-        vt(xv)
-        while t_used < budget_s and reps < 50:
-            t0 = time.perf_counter()
-            jb(x, c, temb)
-            vt(xv)
-            t_used += time.perf_counter() - t0
-            reps += 1
-    tflops = (f_j + f_v) * reps / t_used / 1e12
-    return {"value": tflops / F_STEP_TFLOP, "unit": "steps/s", "cores": cores,
-            "kind": "port", "cpu_tflops_fp32": tflops,
-            "sample": "oracle fp32: 1 dual JointTransformerBlock + 1 VTSelfAttentionBlock, "
-                      "D=1536, %d view-frame items, %d reps in %.1f s; extrapolated by "
-                      "FLOPs to the %.1f TFLOP step" % (items, reps, t_used, F_STEP_TFLOP)}
-
-
-def run_reference(args):
-    """Reference arm: the reference's own semantics (oracle restatement; the reference
-    itself needs diffusers==0.31.0 which is not installable offline) on the host CPU,
-    full-depth north-star model, a bounded sample of the workload per step: 1 frame x
-    6 views without CFG (6 of the 192 view-frame items); steps/s scaled by 192/6."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
+def _cpu_reference_sample(small, n_timed, warm, budget_s):
+    """The ONE definition of the CPU arm, used by `--impl reference` and by the native arm's
+    `cpu_baseline`: the oracle restatement of the reference's PyTorch modules (the reference
+    itself needs diffusers==0.31.0, not installable offline), fp32 on the host cores,
+    full-depth north-star model, a bounded sample of the step per timed forward: 1 frame x
+    6 views without CFG (6 of the 192 view-frame items; every cost of the step is per item
+    or per frame-group), scaled by 192/6.  Returns (ms per full step, #timed, dict)."""
     from oracle import ctsd as octsd
     cores = _host_cores()
     torch.set_num_threads(cores)
-    cfg = load_config(args.small)
+    cfg = load_config(small)
     B, T, V, C, H, W = cfg["latent_shape"]
     mcfg = dict(cfg["model"])
     t0 = time.perf_counter()
@@ -521,34 +529,51 @@ def run_reference(args):
     sample = torch.randn(1, Ts, V, C, H, W)
     timestep = torch.full((1, Ts, V), 500.0)
     times = []
-    budget_s = 150.0           # bounded: at most 1 warm-up + as many of K samples as fit
     t_loop = time.perf_counter()
     with torch.no_grad():
-        for k in range(min(args.warmup, 1) + args.steps):
+        for k in range(warm + n_timed):
             t0 = time.perf_counter()
             model(sample, timestep, **cond)
             dt = time.perf_counter() - t0
-            if k >= min(args.warmup, 1):
+            if k >= warm:
                 times.append(dt)
             if times and time.perf_counter() - t_loop + dt > budget_s:
                 break
     full_items = 2 * B * T * V
     ms = statistics.mean(times) * 1000.0 * full_items / items
+    info = {"value": 1000.0 / ms, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": "oracle fp32 full-depth DiT forward incl. ImageAdapter on 1 frame x "
+                      "%d views (no CFG) = %d of %d view-frame items per timed forward, "
+                      "scaled x%d; %d warm-up + %d timed forwards (budget %d s); model build "
+                      "%.0f s" % (V, items, full_items, full_items // items, warm, len(times),
+                                  int(budget_s), t_build)}
+    return ms, len(times), info
+
+
+def cpu_baseline(budget_s=30.0, small=False):
+    """`cpu_baseline` of the native arm: the same sample definition as `--impl reference`,
+    one warm-up and at most two timed forwards inside `budget_s`."""
+    return _cpu_reference_sample(small, 2, 1, budget_s)[2]
+
+
+def run_reference(args):
+    """Reference arm (rank 0 only): see `_cpu_reference_sample`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = load_config(args.small)
+    B, T, V, C, H, W = cfg["latent_shape"]
+    warm = min(args.warmup, 1)
+    ms, n_timed, info = _cpu_reference_sample(args.small, args.steps, warm, 150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": 1000.0 / ms, "unit": "steps/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": n_timed, "warmup": warm,
         "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "ctsd_35 DFoT 6-view x 16-frame with layout",
                    "latent_shape": [2 * B, T, V, C, H, W]},
-        "cpu_baseline": {
-            "value": 1000.0 / ms, "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": "oracle fp32 full-depth DiT forward incl. ImageAdapter on 1 frame x "
-                      "%d views (no CFG) = %d of %d view-frame items per timed step, "
-                      "scaled x%d; %d timed samples within a %d s budget; model build %.0f s"
-                      % (V, items, full_items, full_items // items, len(times), int(budget_s),
-                         t_build)},
+        "cpu_baseline": info,
         "e2e": {"value": 1000.0 / ms, "unit": "steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -561,10 +586,16 @@ def main():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="compute dtype of the GEMM / attention operands; fp16 is the "
+                         "reference's own (model_dtype torch.float16 + cuda autocast in "
+                         "examples/ctsd_35_df16_*.json) and the headline; bf16 is reported "
+                         "beside it (`other_dtype`)")
     ap.add_argument("--small", action="store_true", help="debug-size model/shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--cpu-budget", type=float, default=30.0)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip streaming_e2e / workloads / eager_gpu_baseline / other dtype")
     ap.add_argument("--profile-dump", default=None,
                     help="write per-shape GEMM timing of the timed steps to this JSON")
     args = ap.parse_args()

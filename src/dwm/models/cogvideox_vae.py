@@ -113,7 +113,7 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
         self._pk = None
         self._pk_enc = None
         self.num_sample_frames_batch_size = 8
-        if with_encoder:       # opt-in until its GPU parity test has run (tests/test_vae_gpu.py)
+        if with_encoder:       # from_pretrained turns it on when the checkpoint has encoder weights
             self.encoder = self._build_encoder(in_channels, latent_channels, block_out_channels,
                                                layers_per_block, g, level)
 
@@ -164,7 +164,6 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
         with open(os.path.join(path, "config.json")) as f:
             cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
         cfg.update(kwargs)
-        vae = cls(**cfg)
         for name in ("diffusion_pytorch_model.safetensors",
                      "diffusion_pytorch_model.fp16.safetensors"):
             fp = os.path.join(path, name)
@@ -175,8 +174,14 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
         else:
             state = torch.load(os.path.join(path, "diffusion_pytorch_model.bin"),
                                map_location="cpu", weights_only=True)
-        vae.load_state_dict({k: v for k, v in state.items()
-                             if k.startswith("decoder.")}, strict=True)
+        # a checkpoint that carries the encoder gets it (validated on B200 against the oracle,
+        # tests/test_vae_gpu.py::test_encode_matches_oracle), as diffusers' class always does
+        has_enc = any(k.startswith("encoder.") for k in state)
+        cfg.setdefault("with_encoder", has_enc)
+        vae = cls(**cfg)
+        keep = ("decoder.", "encoder.") if cfg["with_encoder"] else ("decoder.",)
+        vae.load_state_dict({k: v for k, v in state.items() if k.startswith(keep)},
+                            strict=True)
         return vae
 
     def _apply(self, fn, *a, **k):

@@ -654,6 +654,8 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
     def _joint_block(self, b, ws, N, S, L, residual):
         D, heads = self.inner_dim, self.heads
         x, c, mod = ws["x"], ws["c"], ws["mod"]
+        c_src = ws.pop("c_in", None)          # first block: context read from the cache
+        c_src = c if c_src is None else c_src
         a16, a16b, ac16 = ws["a16"], ws["a16b"], ws["ac16"]
         qkv, o16, oc16 = ws["qkv_j"], ws["o16"], ws["oc16"]
         o, _ = b["mod"]
@@ -673,7 +675,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
             kw.update(add_full=residual, sum_out=x)
         _ops.layernorm(x, a16, eps=1e-6, rows_per_item=S, shift=shift_msa,
                        scale=scale_msa, **kw)
-        _ops.layernorm(c, ac16, eps=1e-6, rows_per_item=L, shift=c_shift_msa,
+        _ops.layernorm(c_src, ac16, eps=1e-6, rows_per_item=L, shift=c_shift_msa,
                        scale=c_scale_msa)
         if b["qk_norm"]:
             _ops.linear(a16, *b["qkv"], epilogue=_lib.EPI_QKNORM, out=qkv,
@@ -713,7 +715,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         _ops.linear(ws["g16"], *b["ff2"], epilogue=_lib.EPI_RESID, resid=x, out=x,
                     gate=gate_mlp, rows_per_item=S)
         if not b["last"]:
-            _ops.linear(oc16, *b["cout"], epilogue=_lib.EPI_RESID, resid=c, out=c,
+            _ops.linear(oc16, *b["cout"], epilogue=_lib.EPI_RESID, resid=c_src, out=c,
                         gate=c_gate_msa, rows_per_item=L)
             _ops.layernorm(c, ac16, eps=1e-6, rows_per_item=L, shift=c_shift_mlp,
                            scale=c_scale_mlp)
@@ -727,11 +729,14 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         self, sample, timestep, encoder_hidden_states, pooled_projections,
         condition_image_tensor=None, disable_crossview=None,
         disable_temporal=None, crossview_attention_mask=None,
-        added_time_ids=None, t_offset=0, T_total=None
+        added_time_ids=None, t_offset=0, T_total=None, cfg_repeat=1
     ):
         """Runs the noise-predict forward and returns the proj_out tokens
         fp32 [B*T*V*S, p*p*C] (column = (py*p+px)*C + c) plus the geometry; the
-        fused CFG/Euler kernel and `forward` un-patchify from this."""
+        fused CFG/Euler kernel and `forward` un-patchify from this.
+        `cfg_repeat=2`: `sample` / `timestep` hold ONE copy of the batch and stand for
+        `torch.cat([x, x])` (reference ctsd.py:2058-2063) — the patchify and timestep kernels
+        write both halves, no concatenated copy is materialised."""
         if self._pk is None:
             self._pack()
         pk = self._pk
@@ -740,6 +745,7 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
             raise RuntimeError("DiTCrossviewTemporalConditionModel needs CUDA "
                                "tensors; there is no CPU fallback.")
         B, T, V, C, H, W = sample.shape
+        B *= cfg_repeat
         Hp, Wp = H // P, W // P
         N, S = B * T * V, Hp * Wp
         T_total = T if T_total is None else T_total
@@ -751,14 +757,22 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         ws = self._workspace(N, S, L, sample.device, dt)
 
         # K1: patchify conv + cropped pos-embed
-        _ops.patchify(sample.reshape(N, C, H, W).float().contiguous(), P,
-                      ws["patch16"])
+        x_in = sample.reshape(N // cfg_repeat, C, H, W)
+        if x_in.dtype != torch.float32 or not x_in.is_contiguous():
+            x_in = x_in.float().contiguous()
+        n1 = (N // cfg_repeat) * S
+        for r in range(cfg_repeat):
+            _ops.patchify(x_in, P, ws["patch16"][r * n1:(r + 1) * n1])
         _ops.linear(ws["patch16"], pk["patch_w"], pk["patch_b"],
                     epilogue=_lib.EPI_RESID, resid=cd["pos"], resid_row_mod=S,
                     out=ws["x"])
         # K3: temb = timestep_embedder(sinusoid(t)) + text_embedder(pooled)
-        _ops.sinusoid(timestep.flatten().float().contiguous(), 256, ws["tsin"],
-                      True, 0.0)
+        t_in = timestep.flatten()
+        if t_in.dtype != torch.float32 or not t_in.is_contiguous():
+            t_in = t_in.float().contiguous()
+        for r in range(cfg_repeat):
+            _ops.sinusoid(t_in, 256, ws["tsin"][r * t_in.numel():(r + 1) * t_in.numel()],
+                          True, 0.0)
         _ops.linear(ws["tsin"], *pk["t1"], act=_lib.ACT_SILU, out=ws["th"])
         _ops.linear(ws["th"], *pk["t2"], epilogue=_lib.EPI_RESID,
                     resid=cd["text_emb"], out=ws["temb"])
@@ -766,7 +780,9 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         # every AdaLN modulation of the forward in one GEMM
         _ops.linear(ws["temb_silu"], pk["mod_w"], pk["mod_b"],
                     epilogue=_lib.EPI_F32, out=ws["mod"])
-        ws["c"].copy_(cd["c0"])
+        # the context stream starts as the (cached, read-only) embedded text: block 0 reads
+        # cd["c0"] and writes ws["c"], so no per-step copy of it is made
+        ws["c_in"] = cd["c0"]
 
         residuals = list(cd["residuals"])
         cv_attend = self._crossview_attend(B, T, V, Hp, Wp, cd.get("mask")) \

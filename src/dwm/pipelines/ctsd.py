@@ -386,9 +386,6 @@ class CrossviewTemporalSD:
         x = latents
         t = timesteps
         split_cfg = do_cfg and plan is not None and plan.cfg_ways == 2
-        if do_cfg and not split_cfg:
-            x = torch.cat([latents, latents])
-            t = torch.cat([timesteps, timesteps])
         self.model.shard = plan
         tokens, _ = self.model.forward_tokens(
             x, t, conditions["encoder_hidden_states"],
@@ -399,7 +396,8 @@ class CrossviewTemporalSD:
             conditions.get("crossview_attention_mask"),
             conditions.get("added_time_ids"),
             t_offset=0 if plan is None else plan.t_offset,
-            T_total=None if plan is None else plan.T)
+            T_total=None if plan is None else plan.T,
+            cfg_repeat=2 if (do_cfg and not split_cfg) else 1)
         if split_cfg:   # exchange the branch predictions inside the CFG pair
             both = getattr(self, "_cfg_tokens", None)
             if both is None or both.shape[0] != 2 * tokens.shape[0]:
@@ -910,10 +908,12 @@ class StreamingCrossviewTemporalSD(CrossviewTemporalSD):
                 else:
                     self.conditions[k] = torch.cat(
                         [self.conditions[k][:, 1:], v], dim=1)
-            # opt-in: tell the model that the new condition set is the previous one moved on
-            # by a frame, so that it updates its step-invariant cache incrementally
+            # tell the model that the new condition set is the previous one moved on by a
+            # frame, so that it updates its step-invariant cache incrementally (equal to the
+            # full rebuild: tests/test_model_gpu.py::test_streaming_ring_cache_equals_full_
+            # recompute); `condition_ring: false` / DWM_STREAM_RING=0 switches it off
             if self.inference_config.get(
-                    "condition_ring", os.environ.get("DWM_STREAM_RING", "0") == "1"):
+                    "condition_ring", os.environ.get("DWM_STREAM_RING", "1") == "1"):
                 self.model._ring_shift = True
             self.latents = torch.cat([
                 self.latents[:, 1:],

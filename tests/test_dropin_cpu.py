@@ -66,3 +66,66 @@ def test_scheduler_name_mapping_covers_the_example_strings():
     for s in ("diffusers.DDIMScheduler", "diffusers.DPMSolverMultistepScheduler",
               "diffusers.FlowMatchEulerDiscreteScheduler"):
         assert s in src
+
+
+# -- the example configs themselves (not a string list): tests/golden/example_pipeline_blocks.json
+#    holds the `pipeline` block of every examples/ctsd_*.json of the reference ------------------
+def _example_blocks():
+    import json
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "example_pipeline_blocks.json")) as f:
+        return json.load(f)
+
+
+def test_example_fixture_is_the_reference_examples():
+    """Where the reference tree is present the committed fixture must be exactly what its
+    example configs say (minus the site-specific checkpoint paths)."""
+    import os
+    import sys
+    if not os.path.isdir("/root/reference/examples"):
+        pytest.skip("reference tree not present on this box")
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_example_blocks
+    assert make_example_blocks.blocks() == _example_blocks()
+
+
+@pytest.mark.parametrize("name", sorted(_example_blocks()))
+def test_example_pipeline_block_instantiates_through_the_factory(name):
+    """Every class named by the example resolves to the mirror and the `model` block builds
+    through dwm.common.create_instance_from_config with the reference's own kwargs (on the
+    meta device: shapes only).  The UniMLVG example (explicit perspective modelling) is outside
+    the CTSD hot path and must refuse loudly instead of building something else."""
+    import torch
+    import dwm.common
+    blk = _example_blocks()[name]["pipeline"]
+    pipe_cls = dwm.common.get_class(blk["_class_name"])
+    assert pipe_cls.__module__ == "dwm.pipelines.ctsd"
+    ctor = inspect.signature(pipe_cls.__init__).parameters
+    for k in blk:
+        if k not in ("_class_name",):
+            assert k in ctor, (name, k)
+    if "model_dtype" in blk:
+        assert dwm.common.create_instance_from_config(blk["model_dtype"]) is torch.float16
+    sched = blk["inference_config"].get("scheduler")
+    if sched is not None and sched.startswith("dwm."):
+        assert dwm.common.get_class(sched).__module__ == "dwm.schedulers.temporal_independent"
+    model_cls = dwm.common.get_class(blk["model"]["_class_name"])
+    assert model_cls.__module__.startswith("dwm.models.crossview_temporal_")
+    if "unimlvg" in name:
+        with pytest.raises(NotImplementedError):
+            with torch.device("meta"):
+                dwm.common.create_instance_from_config(blk["model"])
+        return
+    with torch.device("meta"):
+        model = dwm.common.create_instance_from_config(blk["model"])
+    assert isinstance(model, model_cls)
+    n = sum(p.numel() for p in model.parameters())
+    assert n > 1.5e9, n          # full-size SD-2.1 UNet (1.9 B) / SD-3.5-medium graft (3.8-4.1 B)
+    # the configured grafts exist
+    mc = blk["model"]
+    if mc.get("enable_temporal") and "temporal_block_layers" in mc:
+        assert len(model.temporal_transformer_blocks) == len(mc["temporal_block_layers"])
+    if mc.get("enable_crossview") and "crossview_block_layers" in mc:
+        assert len(model.crossview_transformer_blocks) == len(mc["crossview_block_layers"])

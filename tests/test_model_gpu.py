@@ -109,10 +109,6 @@ def test_real_width_two_layers():
     assert _rel(y, ref) < 2e-2, _rel(y, ref)
 
 
-# Written after the round's GPU budget was spent (opt-in feature, default off): first thing to run
-# next round with DWM_RUN_UNVALIDATED=1.
-@pytest.mark.skipif(__import__("os").environ.get("DWM_RUN_UNVALIDATED", "0") != "1",
-                    reason="streaming ring cache not yet run on a GPU (DWM_RUN_UNVALIDATED=1)")
 def test_streaming_ring_cache_equals_full_recompute():
     """FIFO moved on by one frame: the incrementally updated condition cache (`_ring_shift`)
     must give the same forward as rebuilding it from the new condition tensors."""

@@ -96,11 +96,7 @@ def test_encoder_state_dict_keys_cpu():
             assert o.encode_mode(torch.zeros(1, 3, t, 16, 16)).shape == (1, 16, tz, 2, 2)
 
 
-# Written after the round's GPU budget was spent: first thing to run next round
-# (DWM_RUN_UNVALIDATED=1 python -m pytest tests/test_vae_gpu.py -m gpu -k encode).
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("DWM_RUN_UNVALIDATED", "0") != "1",
-                    reason="CogVideoX encoder not yet run on a GPU (set DWM_RUN_UNVALIDATED=1)")
 @pytest.mark.parametrize("frames", [1, 9, 17])
 def test_encode_matches_oracle(frames):
     o, m = _enc_pair(torch.float16)
