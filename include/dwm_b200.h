@@ -105,11 +105,15 @@ const char* dwm_b200_last_error(void);
 /* Runtime switches (no reference counterpart; they select between kernels that must agree,
  * which tests/ use for kernel-variant parity): "gemm_2cta" = 1 routes dwm_b200_linear (M >= 512) to the 2-CTA
  * cta_group::2 kernel, 0 to the 1-CTA kernel (default: env DWM_GEMM_2CTA, else 1);
- * "attn_tc" routes eligible (contiguous, unmasked, head_dim 64) attention: 2 = tcgen05
- * kernel with two co-resident CTAs per SM and O in TMEM (default), 1 = first-generation
- * tcgen05 kernel, 0 = mma.sync kernel, -1 = re-read env DWM_ATTN_TC / DWM_ATTN_LEGACY;
+ * "attn_tc" routes eligible head_dim-64 attention (contiguous sequences; gathered sequences of
+ * whole `inner`-token units with an optional unit mask): 2 = tcgen05 kernel with two
+ * co-resident CTAs per SM and O in TMEM (default), 0 = mma.sync kernel, -1 = re-read env
+ * DWM_ATTN_TC / DWM_ATTN_LEGACY;
  * "ln_staged" = 1 (default) runs large LayerNorms through the bulk-copy staged kernel, 0
- * keeps the register-resident kernel. */
+ * keeps the register-resident kernel;
+ * "resid_tma" = 1 (default) stages the fp32 residual tile of DWM_EPI_RESID through shared
+ * memory with TMA loads and stores (2-CTA kernel, plain [M,N] residual), 0 keeps the
+ * register / transposing epilogue. */
 int dwm_b200_set_option(const char* name, int value);
 
 /* y = epilogue(A @ W^T): replaces every torch.nn.Linear / 1x1 / patchify conv on the

@@ -334,11 +334,12 @@ static int launch_attn(const AttnParams& p, cudaStream_t s) {
   return 0;
 }
 
-// attention_tc.cu
+// attention_tc2.cu (tcgen05: two co-resident CTAs per SM, O in TMEM): contiguous sequences
+// and gathered unit sequences (cross-view / temporal row-wise, optional unit mask)
 bool attn_tc_eligible(const dwm_attention_args* a);
-int attn_tc_launch(const dwm_attention_args* a, cudaStream_t s);
-// attention_tc2.cu (two co-resident CTAs per SM, O in TMEM)
+bool attn_tcg_eligible(const dwm_attention_args* a);
 int attn_tc2_launch(const dwm_attention_args* a, cudaStream_t s);
+int attn_tcg_launch(const dwm_attention_args* a, cudaStream_t s);
 
 }  // namespace dwm
 
@@ -358,13 +359,15 @@ extern "C" int dwm_b200_attention(const dwm_attention_args* a, dwm_stream_t stre
     DWM_REQUIRE(a->out2 && a->ldo2 % 8 == 0 && a->split < a->seq, "dwm_b200_attention: bad split/out2");
   if (a->mask) DWM_REQUIRE(a->mask_div > 0 && a->n_outer > 0, "dwm_b200_attention: mask needs mask_div, n_outer");
   {
-    // contiguous, unmasked sequences (joint / dual attention) run on tcgen05 + TMEM
-    if (g_attn_tc < 0) {   // env DWM_ATTN_TC = 0 | 1 | 2 (DWM_ATTN_LEGACY: same as 0); default 2
+    // contiguous sequences (joint / dual attention) and gathered unit sequences (cross-view /
+    // temporal row-wise) run on tcgen05 + TMEM; the rest (pointwise temporal, separate K,V,
+    // short sequences) on the mma.sync kernel below
+    if (g_attn_tc < 0) {   // env DWM_ATTN_TC = 0 | 2 (DWM_ATTN_LEGACY: same as 0); default 2
       const char* e = getenv("DWM_ATTN_TC");
       g_attn_tc = getenv("DWM_ATTN_LEGACY") != nullptr ? 0 : (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
     }
-    if (g_attn_tc == 2 && attn_tc_eligible(a)) return attn_tc2_launch(a, reinterpret_cast<cudaStream_t>(stream));
-    if (g_attn_tc == 1 && attn_tc_eligible(a)) return attn_tc_launch(a, reinterpret_cast<cudaStream_t>(stream));
+    if (g_attn_tc >= 1 && attn_tc_eligible(a)) return attn_tc2_launch(a, reinterpret_cast<cudaStream_t>(stream));
+    if (g_attn_tc >= 1 && attn_tcg_eligible(a)) return attn_tcg_launch(a, reinterpret_cast<cudaStream_t>(stream));
   }
   const long long groups = static_cast<long long>(a->group_dims[0]) * a->group_dims[1] * a->group_dims[2];
   if (a->kv)

@@ -19,6 +19,17 @@
 //              against the stale reference max m_ref (values <= 256, exact in fp32 sums and
 //              representable in bf16 / fp16), so the common case touches neither O nor l.
 //              out = O / l is independent of m_ref.
+//
+// Gathered sequences (template flag G): cross-view row-wise attention
+// "(bt v) (h w) c -> (bt h) (v w) c" with its [B,V,V] view mask, and temporal row-wise
+// attention "(b t v) (h w) c -> (b v h) (t w) c" run on the same pipeline.  A sequence is
+// n_out "outer" units (views / frames) of `inner` contiguous tokens (one latent row); a 5-D
+// tensor map (col, w, outer, g1, g0) lets ONE bulk tensor load fetch a tile of `upt` whole
+// units (upt * inner <= 128 rows) straight from the un-permuted q|k|v buffer — the
+// reference's two 264 MB permutes and its [512,168,168] mask never exist.  The view mask is
+// a per-row bit set over key units, expanded once per key block to a 128-bit column mask.
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/dwm_b200.h"
 
@@ -42,6 +53,10 @@ struct AttnTc2Params {
   void* out; long long ldo; long long out_group_stride;
   int split; void* out2; long long ldo2;
   float scale_log2;
+  // gathered sequences (G): group g = g0 * g1n + i1
+  int inner, n_out, upt, g1n;
+  long long out_gs1, out_so;
+  const unsigned char* mask; int mask_div, mask_n;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_sw128_mn2(uint32_t smem_addr) {
@@ -60,7 +75,7 @@ __device__ __forceinline__ float ex2_approx2(float x) {
   return y;
 }
 
-template <typename T>
+template <typename T, bool G>
 __global__ void __launch_bounds__(tc2::THREADS, 2)
     attn_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const AttnTc2Params p) {
   using namespace tc2;
@@ -91,6 +106,14 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.groups * p.heads * p.q_tiles;
+  // G: a tile holds upt * inner <= 128 rows; the rows behind them are never written by TMA and
+  // must be finite (P = 0 times a stale NaN in V would poison O): zero all tiles once
+  const uint32_t tile_tx = G ? static_cast<uint32_t>(p.upt * p.inner * 128) : static_cast<uint32_t>(TILE);
+  if constexpr (G) {
+    uint4* z = reinterpret_cast<uint4*>(sq);
+    for (int i = threadIdx.x; i < TILES_BYTES / 16; i += THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap);
@@ -130,15 +153,22 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
         int g, h, qt;
         decode(w, g, h, qt);
         const int row0 = static_cast<int>(g * p.group_stride);
+        const int g0 = G ? g / p.g1n : 0, i1 = G ? g - g0 * p.g1n : 0;
         mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, TILE);
-        tma_load_2d(&tmap, q_full, sq, h * HD, row0 + qt * BQ, kEvictFirst);
+        mbar_expect_tx(q_full, tile_tx);
+        if constexpr (G) tma_load_5d(&tmap, q_full, sq, h * HD, 0, qt * p.upt, i1, g0, kEvictFirst);
+        else tma_load_2d(&tmap, q_full, sq, h * HD, row0 + qt * BQ, kEvictFirst);
         for (int kb = 0; kb < p.n_kb; ++kb) {
           mbar_wait(&kv_empty[kvs], kvph ^ 1);
-          mbar_expect_tx(&kv_full[kvs], 2 * TILE);
+          mbar_expect_tx(&kv_full[kvs], 2 * tile_tx);
           uint8_t* st = skv + kvs * 2 * TILE;
-          tma_load_2d(&tmap, &kv_full[kvs], st, p.D + h * HD, row0 + kb * BK, kEvictLast);
-          tma_load_2d(&tmap, &kv_full[kvs], st + TILE, 2 * p.D + h * HD, row0 + kb * BK, kEvictLast);
+          if constexpr (G) {
+            tma_load_5d(&tmap, &kv_full[kvs], st, p.D + h * HD, 0, kb * p.upt, i1, g0, kEvictLast);
+            tma_load_5d(&tmap, &kv_full[kvs], st + TILE, 2 * p.D + h * HD, 0, kb * p.upt, i1, g0, kEvictLast);
+          } else {
+            tma_load_2d(&tmap, &kv_full[kvs], st, p.D + h * HD, row0 + kb * BK, kEvictLast);
+            tma_load_2d(&tmap, &kv_full[kvs], st + TILE, 2 * p.D + h * HD, row0 + kb * BK, kEvictLast);
+          }
           if (++kvs == KV_STAGES) { kvs = 0; kvph ^= 1; }
         }
       }
@@ -211,9 +241,42 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
       int g, h, qt;
       decode(w, g, h, qt);
       float m_ref = -INFINITY, l = 0.f;
+      // G: this thread's query token = (outer unit qo, token wi of the unit); `allowed` = key
+      // units it may attend to (the [B,V,V] mask row; everything for padding rows)
+      int qo = 0, wi = 0;
+      bool row_ok = true;
+      uint32_t allowed = 0xffffffffu;
+      if constexpr (G) {
+        const int u = row / p.inner;
+        wi = row - u * p.inner;
+        qo = qt * p.upt + u;
+        row_ok = u < p.upt && qo < p.n_out;
+        if (p.mask && row_ok) {
+          const int g0 = g / p.g1n;
+          const unsigned char* mr = p.mask + (static_cast<long long>(g0 / p.mask_div) * p.mask_n + qo) * p.mask_n;
+          allowed = 0u;
+          for (int ko = 0; ko < p.n_out; ++ko) allowed |= (__ldg(mr + ko) != 0 ? 1u : 0u) << ko;
+        }
+      }
       for (int kb = 0; kb < p.n_kb; ++kb, ++blk) {
         const uint32_t ph = blk & 1;
-        const int kvalid = p.seq - kb * BK;   // keys < kvalid are real
+        int kvalid = p.seq - kb * BK;   // keys < kvalid are real
+        uint32_t cmw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if constexpr (G) {
+          // 128-bit column mask of this key block: unit u2 covers columns [u2*inner, (u2+1)*inner)
+          unsigned __int128 cm = 0;
+          const unsigned __int128 ones = p.inner >= 128 ? ~static_cast<unsigned __int128>(0)
+                                                        : ((static_cast<unsigned __int128>(1) << p.inner) - 1);
+          for (int u2 = 0; u2 < p.upt; ++u2) {
+            const int ko = kb * p.upt + u2;
+            if (ko < p.n_out && ((allowed >> ko) & 1u)) cm |= ones << (u2 * p.inner);
+          }
+          cmw[0] = static_cast<uint32_t>(cm);
+          cmw[1] = static_cast<uint32_t>(cm >> 32);
+          cmw[2] = static_cast<uint32_t>(cm >> 64);
+          cmw[3] = static_cast<uint32_t>(cm >> 96);
+          kvalid = 0;                    // G always takes the masked ("ragged") path
+        }
         mbar_wait(s_full, ph);
         tc_fence_after();
         const bool full = kvalid >= BK;       // warp-uniform: only the last block is ragged
@@ -235,7 +298,7 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (c * 32 + j < kvalid) mx = fmaxf(mx, __uint_as_float(sr[c][j]));
+              if (G ? ((cmw[c] >> j) & 1u) != 0u : (c * 32 + j < kvalid)) mx = fmaxf(mx, __uint_as_float(sr[c][j]));
         }
         // the S buffer is free for the next QK^T as soon as the row sits in registers
         tc_fence_before();
@@ -279,8 +342,8 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
               float p0 = ex2_approx2(fmaf(__uint_as_float(sr[c][j]), sc, -m_ref));
               float p1 = ex2_approx2(fmaf(__uint_as_float(sr[c][j + 1]), sc, -m_ref));
               if (!full) {
-                if (c * 32 + j >= kvalid) p0 = 0.f;
-                if (c * 32 + j + 1 >= kvalid) p1 = 0.f;
+                if (G ? ((cmw[c] >> j) & 1u) == 0u : (c * 32 + j >= kvalid)) p0 = 0.f;
+                if (G ? ((cmw[c] >> (j + 1)) & 1u) == 0u : (c * 32 + j + 1 >= kvalid)) p1 = 0.f;
               }
               rs0 += p0;
               rs1 += p1;
@@ -307,13 +370,19 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       const int j = qt * BQ + row;
-      if (j < p.seq) {
+      if (G ? row_ok : (j < p.seq)) {
         const float inv = 1.0f / l;
         T* dst;
-        if (p.split > 0 && j >= p.split)
+        if constexpr (G) {
+          const int g0 = g / p.g1n, i1 = g - g0 * p.g1n;
+          dst = reinterpret_cast<T*>(p.out) +
+                (static_cast<long long>(g0) * p.out_group_stride + static_cast<long long>(i1) * p.out_gs1 +
+                 static_cast<long long>(qo) * p.out_so + wi) * p.ldo;
+        } else if (p.split > 0 && j >= p.split) {
           dst = reinterpret_cast<T*>(p.out2) + (static_cast<long long>(g) * (p.seq - p.split) + (j - p.split)) * p.ldo2;
-        else
+        } else {
           dst = reinterpret_cast<T*>(p.out) + (static_cast<long long>(g) * p.out_group_stride + j) * p.ldo;
+        }
         dst += h * HD;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -345,26 +414,57 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
   }
 }
 
-template <typename T>
+template <typename T, bool G>
 static int launch_attn_tc2(const dwm_attention_args* a, cudaStream_t s) {
   using namespace tc2;
-  const long long groups = a->group_dims[0];
-  const long long rows_total = groups * a->group_strides[0];
-  CUtensorMap tm;
-  int rc = make_tmap_2d(&tm, a->qkv, rows_total, 3 * a->D, a->ld, 128, 64, 2);
-  if (rc) return rc;
   AttnTc2Params p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap tm;
+  long long groups;
+  if (G) {
+    // merge the (optional) third group dim into the second: row offset i1*gs1 + i2*gs2 with
+    // gs1 == gd2*gs2 is (i1*gd2 + i2)*gs2 (checked by attn_tcg_eligible)
+    const long long gd1 = a->group_dims[1] * a->group_dims[2];
+    const long long gs1 = a->group_dims[2] > 1 ? a->group_strides[2] : a->group_strides[1];
+    const long long ogs1 = a->group_dims[2] > 1 ? a->out_group_strides[2] : a->out_group_strides[1];
+    p.inner = a->inner;
+    p.n_out = a->seq / a->inner;
+    p.upt = 128 / a->inner;
+    if (p.upt > p.n_out) p.upt = p.n_out;
+    p.g1n = static_cast<int>(gd1);
+    p.out_gs1 = ogs1;
+    p.out_so = a->out_stride_outer;
+    p.mask = a->mask; p.mask_div = a->mask_div; p.mask_n = a->n_outer;
+    groups = a->group_dims[0] * gd1;
+    const uint64_t eb = 2;
+    const uint64_t dims[5] = {static_cast<uint64_t>(3 * a->D), static_cast<uint64_t>(a->inner),
+                              static_cast<uint64_t>(p.n_out), static_cast<uint64_t>(gd1),
+                              static_cast<uint64_t>(a->group_dims[0])};
+    const uint64_t st[4] = {static_cast<uint64_t>(a->ld) * eb, static_cast<uint64_t>(a->stride_outer * a->ld) * eb,
+                            static_cast<uint64_t>(gs1 * a->ld) * eb,
+                            static_cast<uint64_t>(a->group_strides[0] * a->ld) * eb};
+    const uint32_t box[5] = {64u, static_cast<uint32_t>(a->inner), static_cast<uint32_t>(p.upt), 1u, 1u};
+    int rc = make_tmap_nd(&tm, a->qkv, 5, dims, st, box, 2);
+    if (rc) return rc;
+    p.q_tiles = (p.n_out + p.upt - 1) / p.upt;
+    p.n_kb = p.q_tiles;
+  } else {
+    groups = a->group_dims[0];
+    const long long rows_total = groups * a->group_strides[0];
+    int rc = make_tmap_2d(&tm, a->qkv, rows_total, 3 * a->D, a->ld, 128, 64, 2);
+    if (rc) return rc;
+    p.q_tiles = (a->seq + BQ - 1) / BQ;
+    p.n_kb = (a->seq + BK - 1) / BK;
+  }
   p.groups = static_cast<int>(groups);
   p.heads = a->heads;
   p.seq = a->seq;
-  p.q_tiles = (a->seq + BQ - 1) / BQ;
-  p.n_kb = (a->seq + BK - 1) / BK;
   p.group_stride = a->group_strides[0];
   p.D = static_cast<int>(a->D);
   p.out = a->out; p.ldo = a->ldo; p.out_group_stride = a->out_group_strides[0];
   p.split = a->split; p.out2 = a->out2; p.ldo2 = a->ldo2;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  auto kern = attn_tc2_kernel<T>;
+  auto kern = attn_tc2_kernel<T, G>;
   static bool attr_set = false;
   if (!attr_set) {
     DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -380,9 +480,41 @@ static int launch_attn_tc2(const dwm_attention_args* a, cudaStream_t s) {
   return 0;
 }
 
+// contiguous, unmasked head_dim-64 sequences (joint / dual attention, UNet spatial attention)
+bool attn_tc_eligible(const dwm_attention_args* a) {
+  return a->kv == nullptr && a->mask == nullptr && a->group_dims[1] == 1 && a->group_dims[2] == 1 &&
+         a->inner == a->seq && a->stride_inner == 1 && a->out_stride_inner == 1 && a->seq > 64 &&
+         a->group_strides[0] >= a->seq && a->group_dims[0] * a->group_strides[0] < (1ll << 31);
+}
+
+// gathered sequences of whole units of `inner` contiguous tokens (cross-view / temporal
+// row-wise), optional [B, n_outer, n_outer] unit mask
+bool attn_tcg_eligible(const dwm_attention_args* a) {
+  if (a->kv != nullptr || a->split > 0 || a->seq <= 64 || a->inner <= 0 || a->inner > 128) return false;
+  if (a->inner == a->seq && a->mask == nullptr) return false;      // contiguous: the 2-D path
+  if (a->seq % a->inner || a->stride_inner != 1 || a->out_stride_inner != 1) return false;
+  const long long n_out = a->seq / a->inner;
+  if (n_out > 32 || n_out > 256) return false;
+  if (a->mask && a->n_outer != n_out) return false;
+  if (a->group_dims[2] > 1 &&
+      (a->group_strides[1] != a->group_dims[2] * a->group_strides[2] ||
+       a->out_group_strides[1] != a->group_dims[2] * a->out_group_strides[2]))
+    return false;
+  if (a->stride_outer <= 0 || a->group_strides[0] <= 0) return false;
+  const long long groups = a->group_dims[0] * a->group_dims[1] * a->group_dims[2];
+  return groups * a->heads * 8 < (1ll << 31);
+}
+
 int attn_tc2_launch(const dwm_attention_args* a, cudaStream_t s) {
-  if (a->dtype == DWM_BF16) return launch_attn_tc2<__nv_bfloat16>(a, s);
-  if (a->dtype == DWM_F16) return launch_attn_tc2<__half>(a, s);
+  if (a->dtype == DWM_BF16) return launch_attn_tc2<__nv_bfloat16, false>(a, s);
+  if (a->dtype == DWM_F16) return launch_attn_tc2<__half, false>(a, s);
+  set_last_error("dwm_b200_attention: dtype must be DWM_BF16 or DWM_F16, got %d", a->dtype);
+  return -1;
+}
+
+int attn_tcg_launch(const dwm_attention_args* a, cudaStream_t s) {
+  if (a->dtype == DWM_BF16) return launch_attn_tc2<__nv_bfloat16, true>(a, s);
+  if (a->dtype == DWM_F16) return launch_attn_tc2<__half, true>(a, s);
   set_last_error("dwm_b200_attention: dtype must be DWM_BF16 or DWM_F16, got %d", a->dtype);
   return -1;
 }

@@ -42,6 +42,9 @@ void set_last_error(const char* fmt, ...);
 int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                  uint64_t ld, uint32_t box_rows, uint32_t box_cols, int elem_bytes);
 
+int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes);
+
 int sm_count();
 
 #ifdef __CUDACC__
@@ -130,6 +133,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+// 5-D box load (implicit-GEMM convolution taps; gathered attention sequences).
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0,
+                                            int c1, int c2, int c3, int c4, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      :
+      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4), "l"(hint)
+      : "memory");
+}
 
 // ---- tcgen05 / TMEM ---------------------------------------------------------
 __device__ __forceinline__ void tc_fence_before() {

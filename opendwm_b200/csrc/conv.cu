@@ -23,17 +23,6 @@ struct ConvGeom {
   int c_in, c_out;
 };
 
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0,
-                                            int c1, int c2, int c3, int c4, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
-      :
-      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-        "r"(c2), "r"(c3), "r"(c4), "l"(hint)
-      : "memory");
-}
-
 template <typename T, int EPI, int CBN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,

@@ -14,11 +14,19 @@
 
 namespace dwm {
 
-constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = 128 * BK * 2;
 constexpr int G2_B_BYTES = 128 * BK * 2;
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+// RT ("residual through TMA") instantiations of the RESID epilogue stage the fp32 residual /
+// result tile through shared memory with TMA in both directions (2 x 4 KB chunk buffers per
+// epilogue warp = 64 KB) and run one operand stage less.
+constexpr int RT_CHUNK_BYTES = 32 * 32 * 4;
+constexpr int RT_EPI_BYTES = EPI_WARPS * 2 * RT_CHUNK_BYTES;
+template <bool RT> struct G2Cfg {
+  static constexpr int kStages = RT ? 5 : 6;
+  static constexpr int kEpiBytes = RT ? RT_EPI_BYTES : EPI_STAGE_BYTES;
+  static constexpr int kSmemBytes = kStages * G2_STAGE_BYTES + kEpiBytes + 1024 + 512;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -78,21 +86,76 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar) {
       : "memory");
 }
 
-template <typename T, int EPI>
+// ---- bulk-tensor store (shared -> global) and its group bookkeeping ------------------------
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// RESID epilogue, TMA in / TMA out (one epilogue warp, one 32-row x 32-column fp32 chunk):
+//   thread = accumulator row (TMEM lane); the residual chunk was brought in by TMA with the
+//   128-byte swizzle (16-byte unit j of row r sits at unit j ^ (r & 7)), so the 32 lanes read
+//   and write their own rows conflict-free and NO transpose is needed; the result leaves through
+//   a bulk tensor store, which also clips the M tail.
+//     v = (acc + bias[n]) * gate[item(m), n] + resid[m, n]
+//     blend: v = alpha[b(m)] * blend_x[m, n] + (1 - alpha[b(m)]) * v
+__device__ __forceinline__ void rt_chunk_math(const uint32_t (&acc)[32], float* rbuf, const float* xbuf,
+                                              const EpiParams& p, int n0, int item, float alpha, int lane) {
+  const float4* b4 = p.bias ? reinterpret_cast<const float4*>(p.bias + n0) : nullptr;
+  const float4* g4 = p.gate ? reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item) * p.gate_ld + n0)
+                            : nullptr;
+  float4* row = reinterpret_cast<float4*>(rbuf) + lane * 8;
+  const float4* xrow = xbuf ? reinterpret_cast<const float4*>(xbuf) + lane * 8 : nullptr;
+  const float a1 = 1.0f - alpha;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int u = j ^ (lane & 7);
+    float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                           __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+    if (b4) {
+      const float4 b = __ldg(b4 + j);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+    if (g4) {
+      const float4 g = __ldg(g4 + j);
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    const float4 r = row[u];
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    if (xrow) {
+      const float4 x = xrow[u];
+      v.x = alpha * x.x + a1 * v.x; v.y = alpha * x.y + a1 * v.y;
+      v.z = alpha * x.z + a1 * v.z; v.w = alpha * x.w + a1 * v.w;
+    }
+    row[u] = v;
+  }
+}
+
+template <typename T, int EPI, bool RT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         int M, int N, int K, EpiParams p) {
+                         const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o,
+                         const __grid_constant__ CUtensorMap tmap_x, int M, int N, int K, EpiParams p) {
+  static_assert(!RT || EPI == DWM_EPI_RESID, "RT is a RESID epilogue variant");
+  constexpr int G2_STAGES = G2Cfg<RT>::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
   float4* epi_stage = reinterpret_cast<float4*>(smem + G2_STAGES * G2_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + G2Cfg<RT>::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + G2_STAGES;
   uint64_t* tfull_bar = bars + 2 * G2_STAGES;
   uint64_t* tempty_bar = bars + 2 * G2_STAGES + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * G2_STAGES + 4);
+  uint64_t* rt_bar = bars + 2 * G2_STAGES + 6;   // RT: 2 per epilogue warp (chunk landed)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -115,6 +178,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
+    }
+    if constexpr (RT) {
+      tma_prefetch_desc(&tmap_r);
+      tma_prefetch_desc(&tmap_o);
+      if (p.blend_x) tma_prefetch_desc(&tmap_x);
+      for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&rt_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -179,6 +248,96 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       }
     }
     __syncwarp();
+  } else if constexpr (RT) {
+    // ========== epilogue, residual tile through TMA (warps 2..9 of both CTAs) ==========
+    // Each warp owns 32 accumulator rows (its TMEM lane quarter) and every second 32-column
+    // chunk of the tile (4 chunks).  Chunks of consecutive tiles form one stream per warp;
+    // without a blend operand the chunk buffers alternate and the load of chunk s+1 is in
+    // flight while chunk s is computed; with a blend operand (K = 6144 launches, long MMAs)
+    // buffer 0 holds the residual / result and buffer 1 the blend operand.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    float* const buf0 = reinterpret_cast<float*>(epi_stage) + ew * 2 * (RT_CHUNK_BYTES / 4);
+    auto bufp = [&](int b) { return buf0 + b * (RT_CHUNK_BYTES / 4); };
+    uint64_t* rb = rt_bar + 2 * ew;
+    const bool blend = p.blend_x != nullptr;
+    const int rpi = static_cast<int>(p.rows_per_item);
+    const int row_off = static_cast<int>(rank) * BM + quarter * 32;
+    auto issue = [&](int tile, int k, int b) {     // lane 0 only
+      const int m0 = (tile / n_blocks) * 2 * BM + row_off;
+      const int n0 = (tile % n_blocks) * BN + (half + 2 * k) * 32;
+      mbar_expect_tx(&rb[b], blend ? 2 * RT_CHUNK_BYTES : RT_CHUNK_BYTES);
+      tma_load_2d(&tmap_r, &rb[b], bufp(b), n0, m0, kEvictFirst);
+      if (blend) tma_load_2d(&tmap_x, &rb[b], bufp(1), n0, m0, kEvictFirst);
+    };
+    // L2 prefetch of a tile's residual / blend rows (512 B per thread), one tile ahead of use
+    auto prefetch_tile = [&](int tile) {
+      if (tile < num_tiles)
+        prefetch_resid_tile<EPI>(p, (tile / n_blocks) * 2 * BM + row_off + lane, M, (tile % n_blocks) * BN, N, half);
+    };
+    uint32_t seq = 0;
+    prefetch_tile(cluster_id);
+    if (cluster_id < num_tiles && lane == 0) issue(cluster_id, 0, 0);
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      const int m_blk = tile / n_blocks;
+      const int n_blk = tile % n_blocks;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      prefetch_tile(tile + n_clusters);
+      const int m = m_blk * 2 * BM + row_off + lane;
+      const int mc = m < M ? m : M - 1;            // tail rows: results are clipped by the store
+      const int item = rpi > 0 ? mc / rpi : 0;
+      const float alpha = blend ? __ldg(p.alpha + (p.rows_per_batch > 0 ? mc / static_cast<int>(p.rows_per_batch) : 0)) : 0.f;
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k, ++seq) {
+        const int cur = blend ? 0 : static_cast<int>(seq & 1);
+        if (!blend && lane == 0) {                 // next chunk of the stream into the other buffer
+          const bool next_here = k < 3;
+          const int ntile = next_here ? tile : tile + n_clusters;
+          if (ntile < num_tiles) {
+            bulk_wait_read0();                     // the store that last read that buffer is done
+            issue(ntile, next_here ? k + 1 : 0, cur ^ 1);
+          }
+        }
+        if (k == 0) {
+          mbar_wait(&tfull_bar[as], aphase);
+          tc_fence_after();
+        }
+        uint32_t acc[32];
+        tmem_ld32(taddr + (half + 2 * k) * 32, acc);
+        mbar_wait(&rb[cur], blend ? (seq & 1) : ((seq >> 1) & 1));
+        tmem_ld_wait();
+        if (k == 3) {                              // accumulator fully read: hand TMEM back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+        }
+        const int n0 = n_blk * BN + (half + 2 * k) * 32;
+        const bool live = n0 < N;                  // chunks past N (N % 256 != 0) only keep the stream in step
+        if (live) rt_chunk_math(acc, bufp(cur), blend ? bufp(1) : nullptr, p, n0, item, alpha, lane);
+        fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) {
+          if (live) {
+            tma_store_2d(&tmap_o, bufp(cur), n0, m_blk * 2 * BM + row_off);
+            bulk_commit();
+          }
+          if (blend) {                             // single-buffered: refill for the next chunk now
+            const bool next_here = k < 3;
+            const int ntile = next_here ? tile : tile + n_clusters;
+            if (ntile < num_tiles) {
+              bulk_wait_read0();
+              issue(ntile, next_here ? k + 1 : 0, 0);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) bulk_wait0();                   // results are in global memory before exit
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9 of both CTAs) =====================
     const int quarter = warp & 3;
@@ -209,19 +368,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
-template <typename T, int EPI>
+int g_resid_tma = -1;   // -1: env DWM_RESID_TMA (default 1); dwm_b200_set_option("resid_tma", 0 | 1)
+
+// The TMA residual path needs a plain [M, N] fp32 residual (row m -> row m), 16-byte pitches
+// and whole 32-column chunks; the pos-embed (row modulo) and per-item residual forms stay on
+// the register path.
+static bool resid_tma_ok(const dwm_linear_args* a) {
+  if (g_resid_tma < 0) {
+    const char* e = getenv("DWM_RESID_TMA");
+    g_resid_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (g_resid_tma != 1 || a->epilogue != DWM_EPI_RESID || !a->resid || a->resid_row_mod != 0) return false;
+  if (a->N % 32 || a->ldr % 4 || a->ldo % 4 || a->ldr < a->N || a->ldo < a->N) return false;
+  if ((reinterpret_cast<uintptr_t>(a->resid) & 15) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return false;
+  if (a->bias && (reinterpret_cast<uintptr_t>(a->bias) & 15)) return false;
+  if (a->gate && ((reinterpret_cast<uintptr_t>(a->gate) & 15) || a->gate_ld % 4)) return false;
+  if (a->blend_x && ((reinterpret_cast<uintptr_t>(a->blend_x) & 15) || a->ldx % 4 || a->ldx < a->N)) return false;
+  return true;
+}
+
+template <typename T, int EPI, bool RT>
 static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tr, to, tx;
   int rc = make_tmap_2d(&ta, a->A, a->M, a->K, a->lda, BM, BK, 2);
   if (rc) return rc;
   rc = make_tmap_2d(&tb, a->W, a->N, a->K, a->ldw, BN / 2, BK, 2);
   if (rc) return rc;
+  if (RT) {
+    rc = make_tmap_2d(&tr, a->resid, a->M, a->N, a->ldr, 32, 32, 4);
+    if (rc) return rc;
+    rc = make_tmap_2d(&to, a->out, a->M, a->N, a->ldo, 32, 32, 4);
+    if (rc) return rc;
+    if (a->blend_x) {
+      rc = make_tmap_2d(&tx, a->blend_x, a->M, a->N, a->ldx, 32, 32, 4);
+      if (rc) return rc;
+    } else {
+      tx = tr;
+    }
+  } else {
+    tr = ta; to = ta; tx = ta;   // unused by the kernel
+  }
   EpiParams p;
   fill_epi_params(p, a);
-  auto kern = gemm2_tcgen05_kernel<T, EPI>;
+  auto kern = gemm2_tcgen05_kernel<T, EPI, RT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<RT>::kSmemBytes));
     attr_set = true;
   }
   const long long m_blocks = (a->M + 2 * BM - 1) / (2 * BM);
@@ -229,8 +421,8 @@ static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
   const long long tiles = m_blocks * n_blocks;
   const int pairs = sm_count() / 2;
   const int clusters = static_cast<int>(tiles < pairs ? tiles : pairs);
-  kern<<<2 * clusters, GEMM_THREADS, G2_SMEM_BYTES, stream>>>(ta, tb, static_cast<int>(a->M), static_cast<int>(a->N),
-                                                             static_cast<int>(a->K), p);
+  kern<<<2 * clusters, GEMM_THREADS, G2Cfg<RT>::kSmemBytes, stream>>>(
+      ta, tb, tr, to, tx, static_cast<int>(a->M), static_cast<int>(a->N), static_cast<int>(a->K), p);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -238,11 +430,13 @@ static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
 template <typename T>
 static int dispatch2(const dwm_linear_args* a, cudaStream_t s) {
   switch (a->epilogue) {
-    case DWM_EPI_STORE: return launch_gemm2<T, DWM_EPI_STORE>(a, s);
-    case DWM_EPI_GEGLU: return launch_gemm2<T, DWM_EPI_GEGLU>(a, s);
-    case DWM_EPI_QKNORM: return launch_gemm2<T, DWM_EPI_QKNORM>(a, s);
-    case DWM_EPI_RESID: return launch_gemm2<T, DWM_EPI_RESID>(a, s);
-    case DWM_EPI_F32: return launch_gemm2<T, DWM_EPI_F32>(a, s);
+    case DWM_EPI_STORE: return launch_gemm2<T, DWM_EPI_STORE, false>(a, s);
+    case DWM_EPI_GEGLU: return launch_gemm2<T, DWM_EPI_GEGLU, false>(a, s);
+    case DWM_EPI_QKNORM: return launch_gemm2<T, DWM_EPI_QKNORM, false>(a, s);
+    case DWM_EPI_RESID:
+      return resid_tma_ok(a) ? launch_gemm2<T, DWM_EPI_RESID, true>(a, s)
+                             : launch_gemm2<T, DWM_EPI_RESID, false>(a, s);
+    case DWM_EPI_F32: return launch_gemm2<T, DWM_EPI_F32, false>(a, s);
     default: set_last_error("dwm_b200_linear: unknown epilogue %d", a->epilogue); return -1;
   }
 }

@@ -26,10 +26,11 @@ def _tol(dtype):
     return 1.2e-2 if dtype == torch.bfloat16 else 2e-3
 
 
-@pytest.fixture(params=[1, 2], ids=["tc1", "tc2"])
+@pytest.fixture(params=[0, 2], ids=["mma", "tc2"])
 def tc_variant(request):
-    """Both tcgen05 attention kernels: 1 = attention_tc.cu (one CTA per SM, O in registers),
-    2 = attention_tc2.cu (two CTAs per SM, O in TMEM with lazy rescale)."""
+    """Both attention kernels: 0 = attention.cu (mma.sync, gathered addressing), 2 =
+    attention_tc2.cu (tcgen05: two CTAs per SM, O in TMEM with lazy rescale; contiguous and
+    gathered-unit sequences)."""
     from opendwm_b200 import lib
     lib.set_option("attn_tc", request.param)
     yield request.param
@@ -54,11 +55,16 @@ def test_joint_split(dtype, tc_variant):
     assert err < _tol(dtype) and err2 < _tol(dtype), (err, err2)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("use_mask", [False, True])
-def test_crossview_rowwise(use_mask):
+@pytest.mark.parametrize("V,W", [(6, 28), (3, 12), (6, 56), (5, 128), (7, 20)])
+def test_crossview_rowwise(use_mask, V, W, dtype, tc_variant):
+    """(bt v) (h w) -> (bt h) (v w) with the [B,V,V] view mask.  V x W = 6 x 28 is the
+    north-star regrouping (seq 168: tiles of 4 + 2 views); 6 x 56 has 2 views per tile, 5 x 128
+    one view per tile, 7 x 20 a ragged last tile, 3 x 12 (seq 36) stays on the small kernel."""
     from opendwm_b200 import ops
-    B, T, V, H, W, heads = 2, 2, 6, 4, 28, 2
-    S, D, dtype = H * W, heads * 64, torch.bfloat16
+    B, T, H, heads = 2, 2, 4, 2
+    S, D = H * W, heads * 64
     qkv = _qkv(B * T * V * S, D, dtype)
     out = torch.zeros(B * T * V * S, D, dtype=dtype, device="cuda")
     ring = torch.zeros(V, V, dtype=torch.bool)
@@ -80,11 +86,14 @@ def test_crossview_rowwise(use_mask):
     assert ((got - ref).abs().max() / ref.abs().max()).item() < _tol(dtype)
 
 
-@pytest.mark.parametrize("T,kind", [(16, "pointwise"), (19, "pointwise"), (5, "pointwise"),
-                                    (5, "rowwise"), (3, "full")])
-def test_temporal(T, kind):
+@pytest.mark.parametrize("T,kind,W", [(16, "pointwise", 6), (19, "pointwise", 6),
+                                      (5, "pointwise", 6), (5, "rowwise", 6), (3, "full", 6),
+                                      (19, "rowwise", 28), (16, "rowwise", 28), (6, "rowwise", 28)])
+def test_temporal(T, kind, W, tc_variant):
+    """Row-wise with W = 28 are the full-size sequences (T x W = 532 / 448 / 168: three group
+    dims, tiles of 4 frames) that take the gathered tcgen05 path."""
     from opendwm_b200 import ops
-    B, V, H, W, heads = 2, 2, 2, 6, 2
+    B, V, H, heads = 2, 2, 2, 2
     S, D, dtype = H * W, heads * 64, torch.bfloat16
     qkv = _qkv(B * T * V * S, D, dtype, seed=T)
     out = torch.zeros(B * T * V * S, D, dtype=dtype, device="cuda")

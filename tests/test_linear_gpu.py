@@ -150,3 +150,59 @@ def test_errors_are_loud():
         ops.linear(a, w)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.linear(a.cpu(), w.cpu())
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [
+    (512, 256, 64),            # one tile per cluster
+    (3 * 448 + 77, 1536, 256),  # M tail (not a multiple of 32), 6 N-tiles
+    (700, 320, 192),           # N % 256 != 0: dead chunks keep the stream in step
+    (148 * 256 + 999, 512, 128),   # > 74 clusters' worth of tiles: multi-tile chunk streams
+    (5376, 1536, 1536),        # north-star out-proj shape (one frame group)
+])
+def test_resid_tma_epilogue_equals_register_epilogue(M, N, K, dtype, gemm_variant):
+    """RESID epilogue with the residual tile staged through TMA (load + store, `resid_tma` = 1,
+    2-CTA kernel) against the register/transposing epilogue and against fp32 PyTorch: plain
+    residual, in place, separate output, gate, bias, AlphaBlender; the two kernels must agree
+    bit for bit (same operation order)."""
+    from opendwm_b200 import ops, lib
+    S = 50
+    items = (M + S - 1) // S
+    B = 2
+    rpb = (M + B - 1) // B
+    a = _mk((M, K), dtype, seed=1)
+    w = _mk((N, K), dtype, 0.05, seed=2)
+    b = _mk((N,), torch.float32, seed=3)
+    resid = _mk((M, N), torch.float32, seed=4)
+    gate = _mk((items, 2 * N), torch.float32, seed=5)[:, N:]
+    x = _mk((M, N), torch.float32, seed=6)
+    alpha = torch.tensor([0.3, 1.0], device="cuda")
+    z = a.float() @ w.float().t() + b
+    rows = torch.arange(M, device="cuda")
+    ref_gate = resid + gate[rows // S] * z
+    al = alpha[rows // rpb][:, None]
+    ref_blend = al * x + (1 - al) * (resid + z)
+
+    def run(tma):
+        lib.set_option("resid_tma", tma)
+        try:
+            y1 = ops.linear(a, w, b, epilogue=lib.EPI_RESID, resid=resid, gate=gate,
+                            rows_per_item=S)
+            r2 = resid.clone()
+            ops.linear(a, w, b, epilogue=lib.EPI_RESID, resid=r2, out=r2, gate=gate,
+                       rows_per_item=S)
+            y3 = ops.linear(a, w, b, epilogue=lib.EPI_RESID, resid=resid, blend_x=x,
+                            alpha=alpha, rows_per_batch=rpb)
+            x4 = x.clone()          # VT-block form: out = blend operand, in place
+            ops.linear(a, w, b, epilogue=lib.EPI_RESID, resid=resid, out=x4, blend_x=x4,
+                       alpha=alpha, rows_per_batch=rpb)
+            y5 = ops.linear(a, w, None, epilogue=lib.EPI_RESID, resid=resid)
+            torch.cuda.synchronize()
+            return y1, r2, y3, x4, y5
+        finally:
+            lib.set_option("resid_tma", 1)
+    new, old = run(1), run(0)
+    for got, ref in zip(new, (ref_gate, ref_gate, ref_blend, ref_blend, resid + z - b)):
+        assert _relerr(got, ref) < 2e-5
+    for g, o in zip(new, old):
+        assert torch.equal(g, o)

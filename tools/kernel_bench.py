@@ -35,13 +35,49 @@ def main():
     fl = 4.0 * (S + L) ** 2 * D * N
     qs = torch.randn(N * S, 3 * D, device="cuda").to(dt)
     f2 = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[N], group_strides=[S], seq=S)
-    for variant, tag in ((1, ""), (2, "_tc2")):
+    t = timeit(f)
+    res["joint_attention_tc2"] = dict(ms=t, tflops=fl / t / 1e9)
+    t = timeit(f2)
+    res["dual_attention_tc2"] = dict(ms=t, tflops=4.0 * S * S * D * N / t / 1e9)
+    # cross-view row-wise (bt h) x (v w) = 512 x 168 with the ring view mask: gathered tcgen05
+    # kernel vs the mma.sync kernel; HBM floor = q|k|v read + out written
+    Bc, Tc, Vc, Hp, Wp = 2, 16, 6, 16, 28
+    ring = torch.zeros(Vc, Vc, dtype=torch.uint8)
+    for i in range(Vc):
+        for d in (-1, 0, 1):
+            ring[i, (i + d) % Vc] = 1
+    mask = ring.unsqueeze(0).repeat(Bc, 1, 1).cuda().contiguous()
+    fcv = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[Bc * Tc, Hp],
+                                group_strides=[Vc * S, Wp], seq=Vc * Wp, inner=Wp,
+                                stride_outer=S, stride_inner=1, mask=mask, mask_div=Tc)
+    byts = qs.numel() * 2 + o.numel() * 2
+    for variant, tag in ((0, "_mma"), (2, "_tc2")):
         lib.set_option("attn_tc", variant)
-        t = timeit(f)
-        res["joint_attention" + tag] = dict(ms=t, tflops=fl / t / 1e9)
-        t = timeit(f2)
-        res["dual_attention" + tag] = dict(ms=t, tflops=4.0 * S * S * D * N / t / 1e9)
+        t = timeit(fcv)
+        res["crossview_attention" + tag] = dict(ms=t, gbs=byts / t / 1e6,
+                                                tflops=4.0 * (Vc * Wp) ** 2 * 64 * heads * Bc * Tc * Hp / t / 1e9)
     lib.set_option("attn_tc", -1)
+    # out-projection RESID GEMM (86016 x 1536 x 1536, gated, in place): TMA-staged residual
+    # epilogue vs the register / transposing one
+    xr = torch.randn(N * S, D, device="cuda")
+    wo = (torch.randn(D, D, device="cuda") * 0.02).to(dt)
+    bo = torch.zeros(D, device="cuda")
+    gate = torch.randn(N, D, device="cuda")
+    o16 = torch.randn(N * S, D, device="cuda").to(dt)
+    fr = lambda: ops.linear(o16, wo, bo, epilogue=lib.EPI_RESID, resid=xr, out=xr, gate=gate,
+                            rows_per_item=S)
+    g16 = torch.randn(N * S, 4 * D, device="cuda").to(dt)
+    w2 = (torch.randn(D, 4 * D, device="cuda") * 0.01).to(dt)
+    fr2 = lambda: ops.linear(g16, w2, bo, epilogue=lib.EPI_RESID, resid=xr, out=xr, gate=gate,
+                             rows_per_item=S)
+    for variant, tag in ((0, "_regs"), (1, "_tma")):
+        lib.set_option("resid_tma", variant)
+        t = timeit(fr)
+        res["resid_gemm_k1536" + tag] = dict(ms=t, tflops=2.0 * N * S * D * D / t / 1e9)
+        t = timeit(fr2)
+        res["resid_gemm_k6144" + tag] = dict(ms=t, tflops=2.0 * N * S * D * 4 * D / t / 1e9)
+    lib.set_option("resid_tma", 1)
+    del g16, w2, o16, xr
     # temporal pointwise (B'=2, T=16, V=6)
     B, T, V = 2, 16, 6
     f = lambda: ops.attention(qs, o, D=D, heads=heads, group_dims=[B, V * S],
