@@ -154,6 +154,28 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
         decode(w, g, h, qt);
         const int row0 = static_cast<int>(g * p.group_stride);
         const int g0 = G ? g / p.g1n : 0, i1 = G ? g - g0 * p.g1n : 0;
+        // the NEXT item's Q / K / V boxes start their trip from HBM to L2 now: its loads can
+        // only be issued once this item's P·V MMAs have released the K,V stages, and with 2..5
+        // key blocks per item that latency would otherwise be exposed once per item
+        if (w + static_cast<int>(gridDim.x) < n_items) {
+          int g2, h2, qt2;
+          decode(w + gridDim.x, g2, h2, qt2);
+          if constexpr (G) {
+            const int g02 = g2 / p.g1n, i12 = g2 - g02 * p.g1n;
+            tma_prefetch_5d(&tmap, h2 * HD, 0, qt2 * p.upt, i12, g02);
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+              tma_prefetch_5d(&tmap, p.D + h2 * HD, 0, kb * p.upt, i12, g02);
+              tma_prefetch_5d(&tmap, 2 * p.D + h2 * HD, 0, kb * p.upt, i12, g02);
+            }
+          } else {
+            const int r2 = static_cast<int>(g2 * p.group_stride);
+            tma_prefetch_2d(&tmap, h2 * HD, r2 + qt2 * BQ);
+            for (int kb = 0; kb < p.n_kb; ++kb) {
+              tma_prefetch_2d(&tmap, p.D + h2 * HD, r2 + kb * BK);
+              tma_prefetch_2d(&tmap, 2 * p.D + h2 * HD, r2 + kb * BK);
+            }
+          }
+        }
         mbar_wait(q_empty, (it & 1) ^ 1);
         mbar_expect_tx(q_full, tile_tx);
         if constexpr (G) tma_load_5d(&tmap, q_full, sq, h * HD, 0, qt * p.upt, i1, g0, kEvictFirst);
@@ -307,7 +329,9 @@ __global__ void __launch_bounds__(tc2::THREADS, 2)
         const float m_new = fmaxf(m_ref, mx * sc);
         // lazy rescale: warp-uniform decision, per-row factor
         if (__any_sync(0xffffffffu, m_new - m_ref > RESCALE_LOG2)) {
-          const float corr = ex2_approx2(m_ref - m_new);   // 0 on the first block (m_ref = -inf)
+          // 0 on the first block (m_ref = -inf); a row whose keys were all masked so far
+          // (m_new = -inf, G only) keeps l = 0 / O = 0 instead of picking up inf - inf
+          const float corr = m_new == -INFINITY ? 1.0f : ex2_approx2(m_ref - m_new);
           l *= corr;
           m_ref = m_new;
           if (kb > 0) {

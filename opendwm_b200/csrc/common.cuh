@@ -133,6 +133,19 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+// L2 prefetch of a tensor-map box (no shared-memory destination, no completion tracking).
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 // 5-D box load (implicit-GEMM convolution taps; gathered attention sequences).
 __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* smem, int c0,
                                             int c1, int c2, int c3, int c4, uint64_t hint) {

@@ -15,17 +15,21 @@
 namespace dwm {
 
 constexpr int G2_A_BYTES = 128 * BK * 2;
-constexpr int G2_B_BYTES = 128 * BK * 2;
-constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 // RT ("residual through TMA") instantiations of the RESID epilogue stage the fp32 residual /
 // result tile through shared memory with TMA in both directions (2 x 4 KB chunk buffers per
 // epilogue warp = 64 KB) and run one operand stage less.
 constexpr int RT_CHUNK_BYTES = 32 * 32 * 4;
 constexpr int RT_EPI_BYTES = EPI_WARPS * 2 * RT_CHUNK_BYTES;
-template <bool RT> struct G2Cfg {
-  static constexpr int kStages = RT ? 5 : 6;
+// BNT = accumulator columns of a tile: 256, or 128 for RT launches whose 256-wide tiling would
+// leave a large tail wave on the 74 clusters (N = 1536 at M = 10 752 rows per rank: 252 tiles =
+// 3.4 waves -> 504 tiles = 6.8 waves).  Per MMA step a CTA then reads 4 KB (A) + 2 KB (W half)
+// per 64 cycles = 96 B/clk of shared memory instead of 64 B/clk.
+template <bool RT, int BNT> struct G2Cfg {
+  static constexpr int kBBytes = (BNT / 2) * BK * 2;
+  static constexpr int kStageBytes = G2_A_BYTES + kBBytes;
+  static constexpr int kStages = RT ? (BNT == 128 ? 6 : 5) : 6;
   static constexpr int kEpiBytes = RT ? RT_EPI_BYTES : EPI_STAGE_BYTES;
-  static constexpr int kSmemBytes = kStages * G2_STAGE_BYTES + kEpiBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -105,25 +109,39 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 //   a bulk tensor store, which also clips the M tail.
 //     v = (acc + bias[n]) * gate[item(m), n] + resid[m, n]
 //     blend: v = alpha[b(m)] * blend_x[m, n] + (1 - alpha[b(m)]) * v
-__device__ __forceinline__ void rt_chunk_math(const uint32_t (&acc)[32], float* rbuf, const float* xbuf,
-                                              const EpiParams& p, int n0, int item, float alpha, int lane) {
-  const float4* b4 = p.bias ? reinterpret_cast<const float4*>(p.bias + n0) : nullptr;
-  const float4* g4 = p.gate ? reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item) * p.gate_ld + n0)
-                            : nullptr;
+// bias / gate values of one chunk, fetched into registers BEFORE the waits on the accumulator
+// and on the residual chunk so that their L2 latency is hidden behind those waits (ncu r02: the
+// gate multiplies were the top stall of the epilogue when loaded at the point of use)
+struct RtVecs {
+  float4 b[8];
+  float4 g[8];
+};
+__device__ __forceinline__ void rt_load_vecs(RtVecs& v, const EpiParams& p, int n0, int item, bool live) {
+  const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+  const float4* g4 = reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item) * p.gate_ld + n0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v.b[j] = (p.bias && live) ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.g[j] = (p.gate && live) ? __ldg(g4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+}
+__device__ __forceinline__ void rt_chunk_math(const uint32_t (&acc)[32], const RtVecs& vv, float* rbuf,
+                                              const float* xbuf, const EpiParams& p, float alpha, int lane) {
   float4* row = reinterpret_cast<float4*>(rbuf) + lane * 8;
   const float4* xrow = xbuf ? reinterpret_cast<const float4*>(xbuf) + lane * 8 : nullptr;
   const float a1 = 1.0f - alpha;
+  const bool has_b = p.bias != nullptr, has_g = p.gate != nullptr;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int u = j ^ (lane & 7);
     float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
                            __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-    if (b4) {
-      const float4 b = __ldg(b4 + j);
+    if (has_b) {
+      const float4 b = vv.b[j];
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
-    if (g4) {
-      const float4 g = __ldg(g4 + j);
+    if (has_g) {
+      const float4 g = vv.g[j];
       v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
     }
     const float4 r = row[u];
@@ -137,19 +155,23 @@ __device__ __forceinline__ void rt_chunk_math(const uint32_t (&acc)[32], float* 
   }
 }
 
-template <typename T, int EPI, bool RT>
+template <typename T, int EPI, bool RT, int BNT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ CUtensorMap tmap_r, const __grid_constant__ CUtensorMap tmap_o,
                          const __grid_constant__ CUtensorMap tmap_x, int M, int N, int K, EpiParams p) {
   static_assert(!RT || EPI == DWM_EPI_RESID, "RT is a RESID epilogue variant");
-  constexpr int G2_STAGES = G2Cfg<RT>::kStages;
+  static_assert(BNT == 256 || (RT && BNT == 128), "narrow tiles exist for the RT epilogue only");
+  using Cfg = G2Cfg<RT, BNT>;
+  constexpr int G2_STAGES = Cfg::kStages;
+  constexpr int G2_B_BYTES = Cfg::kBBytes;
+  constexpr int G2_STAGE_BYTES = Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
   float4* epi_stage = reinterpret_cast<float4*>(smem + G2_STAGES * G2_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + G2Cfg<RT>::kEpiBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES + Cfg::kEpiBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + G2_STAGES;
   uint64_t* tfull_bar = bars + 2 * G2_STAGES;
@@ -164,7 +186,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   const int n_clusters = gridDim.x >> 1;
 
   const int m_blocks = (M + 2 * BM - 1) / (2 * BM);
-  const int n_blocks = (N + BN - 1) / BN;
+  const int n_blocks = (N + BNT - 1) / BNT;
   const int k_blocks = (K + BK - 1) / BK;
   const int num_tiles = m_blocks * n_blocks;
 
@@ -208,7 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           tma_load_2d_2sm(&tmap_a, leader_full, smem_a + stage * G2_A_BYTES, kb * BK,
                           m_blk * 2 * BM + static_cast<int>(rank) * BM, kEvictNormal);
           tma_load_2d_2sm(&tmap_b, leader_full, smem_b + stage * G2_B_BYTES, kb * BK,
-                          n_blk * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
+                          n_blk * BNT + static_cast<int>(rank) * (BNT / 2), kEvictLast);
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -220,7 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(2 * BM, BN, Cvt<T>::kUmmaFmt);
+      constexpr uint32_t idesc = umma_idesc(2 * BM, BNT, Cvt<T>::kUmmaFmt);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -229,7 +251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN;
+        const uint32_t tmem_d = tmem_base + as * BNT;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -266,7 +288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     const int row_off = static_cast<int>(rank) * BM + quarter * 32;
     auto issue = [&](int tile, int k, int b) {     // lane 0 only
       const int m0 = (tile / n_blocks) * 2 * BM + row_off;
-      const int n0 = (tile % n_blocks) * BN + (half + 2 * k) * 32;
+      const int n0 = (tile % n_blocks) * BNT + (half + 2 * k) * 32;
       mbar_expect_tx(&rb[b], blend ? 2 * RT_CHUNK_BYTES : RT_CHUNK_BYTES);
       tma_load_2d(&tmap_r, &rb[b], bufp(b), n0, m0, kEvictFirst);
       if (blend) tma_load_2d(&tmap_x, &rb[b], bufp(1), n0, m0, kEvictFirst);
@@ -274,7 +296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
     // L2 prefetch of a tile's residual / blend rows (512 B per thread), one tile ahead of use
     auto prefetch_tile = [&](int tile) {
       if (tile < num_tiles)
-        prefetch_resid_tile<EPI>(p, (tile / n_blocks) * 2 * BM + row_off + lane, M, (tile % n_blocks) * BN, N, half);
+        prefetch_resid_tile<EPI>(p, (tile / n_blocks) * 2 * BM + row_off + lane, M, (tile % n_blocks) * BNT, N, half, BNT / 2);
     };
     uint32_t seq = 0;
     prefetch_tile(cluster_id);
@@ -290,18 +312,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       const int mc = m < M ? m : M - 1;            // tail rows: results are clipped by the store
       const int item = rpi > 0 ? mc / rpi : 0;
       const float alpha = blend ? __ldg(p.alpha + (p.rows_per_batch > 0 ? mc / static_cast<int>(p.rows_per_batch) : 0)) : 0.f;
-      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + as * BNT + (static_cast<uint32_t>(quarter * 32) << 16);
+      constexpr int NCH = BNT / 64;               // chunks per warp per tile
 #pragma unroll 1
-      for (int k = 0; k < 4; ++k, ++seq) {
+      for (int k = 0; k < NCH; ++k, ++seq) {
         const int cur = blend ? 0 : static_cast<int>(seq & 1);
         if (!blend && lane == 0) {                 // next chunk of the stream into the other buffer
-          const bool next_here = k < 3;
+          const bool next_here = k < NCH - 1;
           const int ntile = next_here ? tile : tile + n_clusters;
           if (ntile < num_tiles) {
             bulk_wait_read0();                     // the store that last read that buffer is done
             issue(ntile, next_here ? k + 1 : 0, cur ^ 1);
           }
         }
+        const int n0 = n_blk * BNT + (half + 2 * k) * 32;
+        const bool live = n0 < N;                  // chunks past N (N % 256 != 0) only keep the stream in step
+        RtVecs vv;
+        rt_load_vecs(vv, p, n0, item, live);
         if (k == 0) {
           mbar_wait(&tfull_bar[as], aphase);
           tc_fence_after();
@@ -310,14 +337,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld32(taddr + (half + 2 * k) * 32, acc);
         mbar_wait(&rb[cur], blend ? (seq & 1) : ((seq >> 1) & 1));
         tmem_ld_wait();
-        if (k == 3) {                              // accumulator fully read: hand TMEM back early
+        if (k == NCH - 1) {                        // accumulator fully read: hand TMEM back early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
         }
-        const int n0 = n_blk * BN + (half + 2 * k) * 32;
-        const bool live = n0 < N;                  // chunks past N (N % 256 != 0) only keep the stream in step
-        if (live) rt_chunk_math(acc, bufp(cur), blend ? bufp(1) : nullptr, p, n0, item, alpha, lane);
+        if (live) rt_chunk_math(acc, vv, bufp(cur), blend ? bufp(1) : nullptr, p, alpha, lane);
         fence_proxy_async();                       // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) {
@@ -326,7 +351,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
             bulk_commit();
           }
           if (blend) {                             // single-buffered: refill for the next chunk now
-            const bool next_here = k < 3;
+            const bool next_here = k < NCH - 1;
             const int ntile = next_here ? tile : tile + n_clusters;
             if (ntile < num_tiles) {
               bulk_wait_read0();
@@ -387,12 +412,32 @@ static bool resid_tma_ok(const dwm_linear_args* a) {
   return true;
 }
 
-template <typename T, int EPI, bool RT>
+int g_gemm_bn = 0;   // dwm_b200_set_option("gemm_bn", 0 = by wave efficiency | 128 | 256)
+
+// Wave efficiency of the persistent schedule on the SM pairs: tiles / (waves * clusters).
+static double wave_eff(long long tiles, int pairs) {
+  const long long waves = (tiles + pairs - 1) / pairs;
+  return static_cast<double>(tiles) / static_cast<double>(waves * pairs);
+}
+// 128-column tiles cost ~50 % more shared-memory operand traffic per FLOP and twice the
+// per-tile bookkeeping, so they are used only where they repair a tail wave by > 6 %.
+static bool narrow_tiles_pay(const dwm_linear_args* a) {
+  if (g_gemm_bn == 128) return true;
+  if (g_gemm_bn == 256) return false;
+  const int pairs = sm_count() / 2;
+  const long long mb = (a->M + 2 * BM - 1) / (2 * BM);
+  const double e256 = wave_eff(mb * ((a->N + 255) / 256), pairs);
+  const double e128 = wave_eff(mb * ((a->N + 127) / 128), pairs);
+  return e128 > e256 + 0.06;
+}
+
+template <typename T, int EPI, bool RT, int BNT>
 static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
+  using Cfg = G2Cfg<RT, BNT>;
   CUtensorMap ta, tb, tr, to, tx;
   int rc = make_tmap_2d(&ta, a->A, a->M, a->K, a->lda, BM, BK, 2);
   if (rc) return rc;
-  rc = make_tmap_2d(&tb, a->W, a->N, a->K, a->ldw, BN / 2, BK, 2);
+  rc = make_tmap_2d(&tb, a->W, a->N, a->K, a->ldw, BNT / 2, BK, 2);
   if (rc) return rc;
   if (RT) {
     rc = make_tmap_2d(&tr, a->resid, a->M, a->N, a->ldr, 32, 32, 4);
@@ -410,18 +455,18 @@ static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
   }
   EpiParams p;
   fill_epi_params(p, a);
-  auto kern = gemm2_tcgen05_kernel<T, EPI, RT>;
+  auto kern = gemm2_tcgen05_kernel<T, EPI, RT, BNT>;
   static bool attr_set = false;
   if (!attr_set) {
-    DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<RT>::kSmemBytes));
+    DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
   const long long m_blocks = (a->M + 2 * BM - 1) / (2 * BM);
-  const long long n_blocks = (a->N + BN - 1) / BN;
+  const long long n_blocks = (a->N + BNT - 1) / BNT;
   const long long tiles = m_blocks * n_blocks;
   const int pairs = sm_count() / 2;
   const int clusters = static_cast<int>(tiles < pairs ? tiles : pairs);
-  kern<<<2 * clusters, GEMM_THREADS, G2Cfg<RT>::kSmemBytes, stream>>>(
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(
       ta, tb, tr, to, tx, static_cast<int>(a->M), static_cast<int>(a->N), static_cast<int>(a->K), p);
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -430,13 +475,14 @@ static int launch_gemm2(const dwm_linear_args* a, cudaStream_t stream) {
 template <typename T>
 static int dispatch2(const dwm_linear_args* a, cudaStream_t s) {
   switch (a->epilogue) {
-    case DWM_EPI_STORE: return launch_gemm2<T, DWM_EPI_STORE, false>(a, s);
-    case DWM_EPI_GEGLU: return launch_gemm2<T, DWM_EPI_GEGLU, false>(a, s);
-    case DWM_EPI_QKNORM: return launch_gemm2<T, DWM_EPI_QKNORM, false>(a, s);
+    case DWM_EPI_STORE: return launch_gemm2<T, DWM_EPI_STORE, false, 256>(a, s);
+    case DWM_EPI_GEGLU: return launch_gemm2<T, DWM_EPI_GEGLU, false, 256>(a, s);
+    case DWM_EPI_QKNORM: return launch_gemm2<T, DWM_EPI_QKNORM, false, 256>(a, s);
     case DWM_EPI_RESID:
-      return resid_tma_ok(a) ? launch_gemm2<T, DWM_EPI_RESID, true>(a, s)
-                             : launch_gemm2<T, DWM_EPI_RESID, false>(a, s);
-    case DWM_EPI_F32: return launch_gemm2<T, DWM_EPI_F32, false>(a, s);
+      if (!resid_tma_ok(a)) return launch_gemm2<T, DWM_EPI_RESID, false, 256>(a, s);
+      return narrow_tiles_pay(a) ? launch_gemm2<T, DWM_EPI_RESID, true, 128>(a, s)
+                                 : launch_gemm2<T, DWM_EPI_RESID, true, 256>(a, s);
+    case DWM_EPI_F32: return launch_gemm2<T, DWM_EPI_F32, false, 256>(a, s);
     default: set_last_error("dwm_b200_linear: unknown epilogue %d", a->epilogue); return -1;
   }
 }

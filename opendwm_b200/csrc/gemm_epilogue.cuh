@@ -306,11 +306,11 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_ba
 // residual (and blend) operand, so the later loads hit L2.
 template <int EPI>
 __device__ __forceinline__ void prefetch_resid_tile(const EpiParams& p, int m, int M, int n_tile0,
-                                                    int N, int half) {
+                                                    int N, int half, int half_cols = BN / 2) {
   if constexpr (EPI == DWM_EPI_RESID) {
-    const int n0 = n_tile0 + half * (BN / 2);
+    const int n0 = n_tile0 + half * half_cols;
     if (m < M && n0 < N) {
-      const int cols = (N - n0) < (BN / 2) ? (N - n0) : (BN / 2);
+      const int cols = (N - n0) < half_cols ? (N - n0) : half_cols;
       const uint32_t bytes = static_cast<uint32_t>(cols) * 4u;
       if (p.resid) {
         if (p.resid_row_mod >= 0) {

@@ -27,12 +27,18 @@ class ShardPlan:
             raise ValueError("world size {} not divisible by {}".format(
                 world, self.cfg_ways))
         self.t_ways = world // self.cfg_ways
-        if frames % self.t_ways:
-            raise ValueError("{} frames not divisible over {} frame shards".format(
+        if frames < self.t_ways:
+            raise ValueError("{} frames cannot feed {} frame shards".format(
                 frames, self.t_ways))
         self.cfg_rank, self.t_rank = rank // self.t_ways, rank % self.t_ways
-        self.T_loc = frames // self.t_ways
-        self.t_offset = self.t_rank * self.T_loc
+        # frame shards may be uneven (5 latent frames of the temporal-VAE config over 4 shards
+        # = 2,1,1,1; 19 frames = 5,5,5,4): the first `frames % t_ways` shards take one more
+        q, rem = divmod(frames, self.t_ways)
+        self.counts = [q + (1 if r < rem else 0) for r in range(self.t_ways)]
+        self.offsets = [sum(self.counts[:r]) for r in range(self.t_ways)]
+        self.T_loc = self.counts[self.t_rank]
+        self.t_offset = self.offsets[self.t_rank]
+        self.even = rem == 0
         self.t_group = self.cfg_group = None
         # K,V exchange of the temporal blocks: fused GEMM-epilogue scatter into peer
         # (symmetric) memory by default, NCCL all-gather with DWM_PEER_SCATTER=0
@@ -78,13 +84,31 @@ class ShardPlan:
         return latents[:, self.frame_slice()].clone(memory_format=torch.contiguous_format)
 
     # ---- collectives -------------------------------------------------------------------
-    def gather_frames_kv(self, kv_local: torch.Tensor, kv_all: torch.Tensor,
-                         async_op: bool = False):
-        """kv_all[r] = kv_local of frame-shard r.  Key position j = r*T_loc + t_loc of a
-        (batch, view, token) group then lives at row
-        r*rows_local + b*(T_loc*V*S) + t_loc*(V*S) + v*S + s of kv_all.view(-1, 2D)."""
-        return dist.all_gather_into_tensor(kv_all, kv_local, group=self.t_group,
-                                           async_op=async_op)
+    def gather_frames_kv(self, kv_local: torch.Tensor, kv_full: torch.Tensor,
+                         batch: int = 1, async_op: bool = False):
+        """NCCL / gloo baseline of the temporal K,V exchange (the default is the fused GEMM-
+        epilogue scatter, `PeerKV`).  kv_local [batch * T_loc * R, C] holds this rank's frames
+        (R rows per frame); kv_full [batch * T * R, C] is the gathered buffer in the UNSHARDED
+        row layout ((b, t, r) -> (b*T + t)*R + r), so the attention kernel addresses keys and
+        values exactly as it does on one GPU whatever the temporal attention type.  Even
+        shards with one batch entry are a plain all-gather into the buffer; otherwise shards
+        are padded to the largest one and copied into place."""
+        C = kv_local.shape[1]
+        R = kv_local.shape[0] // (batch * self.T_loc)
+        if self.even and batch == 1:
+            return dist.all_gather_into_tensor(kv_full, kv_local, group=self.t_group,
+                                               async_op=async_op)
+        t_max = max(self.counts)
+        pad = kv_local.new_zeros(batch, t_max, R, C)
+        pad[:, :self.T_loc] = kv_local.view(batch, self.T_loc, R, C)
+        flat = kv_local.new_empty(self.t_ways * batch, t_max, R, C)
+        dist.all_gather_into_tensor(flat, pad, group=self.t_group)
+        parts = flat.view(self.t_ways, batch, t_max, R, C)
+        full = kv_full.view(batch, self.T, R, C)
+        for r in range(self.t_ways):
+            full[:, self.offsets[r]:self.offsets[r] + self.counts[r]] = \
+                parts[r, :, :self.counts[r]]
+        return _Done() if async_op else None
 
     def gather_cfg_tokens(self, tokens: torch.Tensor, out: torch.Tensor):
         """out = [uncond tokens ; cond tokens] on both ranks of the CFG pair."""
@@ -94,9 +118,18 @@ class ShardPlan:
         """Full [B, T, V, ...] latents from the frame shards (end of window / tests)."""
         if self.t_ways == 1:
             return latents_local
-        parts = [torch.empty_like(latents_local) for _ in range(self.t_ways)]
-        dist.all_gather(parts, latents_local.contiguous(), group=self.t_group)
-        return torch.cat(parts, dim=1)
+        if self.even:
+            parts = [torch.empty_like(latents_local) for _ in range(self.t_ways)]
+            dist.all_gather(parts, latents_local.contiguous(), group=self.t_group)
+            return torch.cat(parts, dim=1)
+        t_max = max(self.counts)
+        shape = list(latents_local.shape)
+        shape[1] = t_max
+        pad = latents_local.new_zeros(shape)
+        pad[:, :self.T_loc] = latents_local
+        parts = [torch.empty_like(pad) for _ in range(self.t_ways)]
+        dist.all_gather(parts, pad, group=self.t_group)
+        return torch.cat([parts[r][:, :self.counts[r]] for r in range(self.t_ways)], dim=1)
 
     def split_call(self, fn, items: torch.Tensor):
         """Item-parallel map over ALL ranks (VAE decode: independent per (batch, view) clip or
@@ -123,37 +156,42 @@ class ShardPlan:
         return torch.cat(parts)[:n]
 
 
+class _Done:
+    """Stand-in for a finished async work handle."""
+    def wait(self):
+        return True
+
+
 class PeerKV:
     """Gathered K,V buffers of a frame group in symmetric (peer-mapped) memory.
 
     Instead of `GEMM -> all_gather`, the K,V projection GEMM of every rank stores its
-    output tiles directly into slot `t_rank` of EVERY peer's buffer (fused epilogue
-    scatter over NVLink, `dwm_linear_args.peer_out`).  Two buffers alternate between
-    consecutive temporal blocks so one group barrier per block is enough: a rank can only
-    start writing buffer b of block k+1 after every peer passed the barrier of block k,
-    i.e. finished reading buffer b in block k-1."""
+    output tiles directly into EVERY peer's buffer (fused epilogue scatter over NVLink,
+    `dwm_linear_args.peer_out`).  The buffers hold the gathered tensor in the UNSHARDED row
+    layout [batch * T * R, width]; a rank's GEMM maps its local row m to row
+    (m / (T_loc*R)) * (T*R) + t_offset*R + m % (T_loc*R) through the epilogue's item
+    mapping, the same on every GPU, so uneven frame shards and every temporal attention type
+    use one addressing.  Two buffers alternate between consecutive temporal blocks so one
+    group barrier per block is enough: a rank can only start writing buffer b of block k+1
+    after every peer passed the barrier of block k, i.e. finished reading buffer b in block
+    k-1."""
 
-    def __init__(self, plan: ShardPlan, rows_local: int, width: int, dtype, device):
+    def __init__(self, plan: ShardPlan, rows_full: int, width: int, dtype, device):
         import torch.distributed._symmetric_memory as symm_mem
         self.plan = plan
-        self.rows_local, self.width = rows_local, width
+        self.rows_full, self.width = rows_full, width
         self.bufs, self.handles = [], []
         for _ in range(2):
-            t = symm_mem.empty(plan.t_ways * rows_local, width, dtype=dtype,
-                               device=device)
+            t = symm_mem.empty(rows_full, width, dtype=dtype, device=device)
             self.bufs.append(t)
             self.handles.append(symm_mem.rendezvous(t, plan.t_group))
-        self.elem = torch.empty((), dtype=dtype).element_size()
         self.turn = 0
 
     def next(self):
-        """(local gathered buffer, local slot view, peer slot pointers, handle)."""
+        """(local gathered buffer, peer buffer base pointers, handle)."""
         b = self.turn
         self.turn ^= 1
         buf, hdl = self.bufs[b], self.handles[b]
-        r = self.plan.t_rank
-        off = r * self.rows_local * self.width * self.elem
-        slot = buf[r * self.rows_local:(r + 1) * self.rows_local]
-        peers = [int(hdl.buffer_ptrs[q]) + off for q in range(self.plan.t_ways)
-                 if q != r]
-        return buf, slot, peers, hdl
+        peers = [int(hdl.buffer_ptrs[q]) for q in range(self.plan.t_ways)
+                 if q != self.plan.t_rank]
+        return buf, peers, hdl

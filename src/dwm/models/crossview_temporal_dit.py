@@ -596,58 +596,81 @@ class DiTCrossviewTemporalConditionModel(_compat.SD3Transformer2DModelMarker):
         return attend
 
     def _temporal_qkv_attend_sharded(self, B, T_loc, V, Hp, Wp, ws):
-        """Frame-sharded temporal attention: K,V of the local frames are projected
-        (+RMSNorm) into a contiguous slab, all-gathered over the frame group while the
-        Q projection runs, then every local query frame attends to all T frames."""
+        """Frame-sharded temporal attention (any temporal_attention_type, even or uneven frame
+        shards): K,V of the local frames are projected (+RMSNorm) straight into the gathered
+        buffer, which keeps the UNSHARDED row layout (b, t, v, s) on every rank — through the
+        GEMM epilogue's item row mapping into local AND peer memory (fused scatter over
+        NVLink), or through an all-gather — while the Q projection runs; then every local
+        query frame attends to all T frames with the single-GPU key addressing."""
         plan = self.shard
-        if self.temporal_attention_type in ("full", "rowwise"):
-            raise NotImplementedError(
-                "frame sharding is implemented for pointwise temporal attention")
         S, D, heads = Hp * Wp, self.inner_dim, self.heads
+        T = plan.T
         rows = B * T_loc * V * S
+        rows_full = B * T * V * S
         dt, dev = ws["a16"].dtype, ws["a16"].device
-        if "kv_loc" not in ws:
+        if ws.get("kv_geom") != (rows, rows_full):
+            ws["kv_geom"] = (rows, rows_full)
             ws["q_loc"] = torch.empty(rows, D, device=dev, dtype=dt)
             ws["peer_kv"] = None
             if plan.use_peer_scatter:
                 from opendwm_b200.sharding import PeerKV
-                ws["peer_kv"] = PeerKV(plan, rows, 2 * D, dt, dev)
-                ws["kv_loc"] = True
+                ws["peer_kv"] = PeerKV(plan, rows_full, 2 * D, dt, dev)
             else:
                 ws["kv_loc"] = torch.empty(rows, 2 * D, device=dev, dtype=dt)
-                ws["kv_all"] = torch.empty(plan.t_ways * rows, 2 * D, device=dev,
-                                           dtype=dt)
+                ws["kv_all"] = torch.empty(rows_full, 2 * D, device=dev, dtype=dt)
         q_loc, peer_kv = ws["q_loc"], ws["peer_kv"]
         eps = 1e-5
+        kind = self.temporal_attention_type
+        # local rows -> rows of the unsharded layout: item = batch entry
+        remap = dict(rows_per_item=T_loc * V * S, out_item_stride=T * V * S,
+                     out_row_offset=plan.t_offset * V * S)
 
-        def project(p, a16, w, b, nw, out, peer_out=None):
+        def project(p, a16, w, b, nw, out, peer_out=None, **kw):
             if p["qk_norm"]:
                 _ops.linear(a16, w, b, epilogue=_lib.EPI_QKNORM, out=out,
                             q_norm_weight=nw, qk_region=D, qk_norm_regions=1,
-                            eps=eps, peer_out=peer_out)
+                            eps=eps, peer_out=peer_out, **kw)
             else:
-                _ops.linear(a16, w, b, out=out, peer_out=peer_out)
+                _ops.linear(a16, w, b, out=out, peer_out=peer_out, **kw)
+
+        def attend(kv_all, out):
+            if kind == "full":         # (b v) (t hw)
+                _ops.attention(
+                    q_loc, out, D=D, heads=heads, group_dims=[B, V],
+                    group_strides=[T_loc * V * S, S], seq=T_loc * S, inner=S,
+                    stride_outer=V * S, stride_inner=1, kv=kv_all, k_col=0, v_col=D,
+                    kv_group_strides=[T * V * S, S], seq_kv=T * S, inner_kv=S,
+                    kv_stride_outer=V * S, kv_stride_inner=1)
+            elif kind == "rowwise":    # (b v h) (t w)
+                _ops.attention(
+                    q_loc, out, D=D, heads=heads, group_dims=[B, V, Hp],
+                    group_strides=[T_loc * V * S, S, Wp], seq=T_loc * Wp, inner=Wp,
+                    stride_outer=V * S, stride_inner=1, kv=kv_all, k_col=0, v_col=D,
+                    kv_group_strides=[T * V * S, S, Wp], seq_kv=T * Wp, inner_kv=Wp,
+                    kv_stride_outer=V * S, kv_stride_inner=1)
+            else:                      # pointwise: (b v hw) t
+                _ops.attention(
+                    q_loc, out, D=D, heads=heads, group_dims=[B, V * S],
+                    group_strides=[T_loc * V * S, 1], seq=T_loc, inner=1,
+                    stride_outer=V * S, stride_inner=0, kv=kv_all, k_col=0, v_col=D,
+                    kv_group_strides=[T * V * S, 1], seq_kv=T, inner_kv=1,
+                    kv_stride_outer=V * S, kv_stride_inner=0)
 
         def qkv_attend(p, a16, out):
             if peer_kv is not None:
                 # fused: the K,V GEMM epilogue scatters its tiles into every peer's
                 # gathered buffer over NVLink; one group barrier publishes them
-                kv_all, slot, peers, hdl = peer_kv.next()
-                project(p, a16, p["kv_w"], p["kv_b"], p.get("nk"), slot, peers)
+                kv_all, peers, hdl = peer_kv.next()
+                project(p, a16, p["kv_w"], p["kv_b"], p.get("nk"), kv_all, peers, **remap)
                 project(p, a16, p["q_w"], p["q_b"], p.get("nq"), q_loc)
                 hdl.barrier(channel=0)
             else:
                 kv_loc, kv_all = ws["kv_loc"], ws["kv_all"]
                 project(p, a16, p["kv_w"], p["kv_b"], p.get("nk"), kv_loc)
-                work = plan.gather_frames_kv(kv_loc, kv_all, async_op=True)
+                work = plan.gather_frames_kv(kv_loc, kv_all, batch=B, async_op=True)
                 project(p, a16, p["q_w"], p["q_b"], p.get("nq"), q_loc)
                 work.wait()
-            _ops.attention(
-                q_loc, out, D=D, heads=heads, group_dims=[B, V * S],
-                group_strides=[T_loc * V * S, 1], seq=T_loc, inner=1,
-                stride_outer=V * S, stride_inner=0, kv=kv_all, k_col=0, v_col=D,
-                kv_group_strides=[T_loc * V * S, 1], seq_kv=plan.T,
-                inner_kv=T_loc, kv_stride_outer=rows, kv_stride_inner=V * S)
+            attend(kv_all, out)
         return qkv_attend
 
     # -- one JointTransformerBlock ----------------------------------------------------------

@@ -344,7 +344,8 @@ class CrossviewTemporalSD:
         configured that holds by construction; otherwise rank 0's seed is broadcast when the
         plan is attached (the reference is single-process and has no such concern)."""
         self._sharding = plan
-        if plan is not None and plan.world > 1 and "generator_seed" not in self.config:
+        if plan is not None and plan.world > 1 and \
+                "generator_seed" not in (getattr(self, "config", None) or {}):
             import torch.distributed as dist
             if not dist.is_initialized():
                 raise RuntimeError("a ShardPlan with world > 1 needs torch.distributed, or "

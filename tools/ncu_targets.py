@@ -17,7 +17,7 @@ from opendwm_b200 import ops, lib
 
 
 def main():
-    dt = torch.bfloat16
+    dt = torch.float16 if os.environ.get("DWM_NCU_DTYPE", "bf16") == "fp16" else torch.bfloat16
     D, heads, N, S, L = 1536, 24, 192, 448, 154
     M = N * S
     dev = "cuda"
@@ -41,7 +41,7 @@ def main():
         for d in (-1, 0, 1):
             ring[i, (i + d) % V] = True
     mask = ring.unsqueeze(0).repeat(B, 1, 1).to(dev).to(torch.uint8).contiguous()
-    todo.append(("cross-view row-wise attention + mask (attn_kernel)", lambda: ops.attention(
+    todo.append(("cross-view row-wise attention + mask (attn_tc2 gathered)", lambda: ops.attention(
         qs, o, D=D, heads=heads, group_dims=[B * T, H], group_strides=[V * S, W], seq=V * W,
         inner=W, stride_outer=S, stride_inner=1, mask=mask, mask_div=T)))
 
@@ -86,6 +86,9 @@ def main():
         ops.spatialnorm_silu(hf, sums, gam, bet, out16, groups=32, eps=1e-6, silu=True)
     todo.append(("GroupNorm stats + apply+SiLU 6x256x448x128", gn))
 
+    only = [t for t in os.environ.get("DWM_NCU_ONLY", "").split(",") if t]
+    if only:      # e.g. DWM_NCU_ONLY="cross-view,out-proj": capture a subset
+        todo = [(n, f) for n, f in todo if any(t in n for t in only)]
     for _, f in todo:
         f()
     torch.cuda.synchronize()
