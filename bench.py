@@ -231,12 +231,19 @@ def run_native(args):
     lat_dev = torch.empty_like(latents)
     idx_dev = torch.empty_like(idx_list[0][0])
 
+    # the end-to-end loop replays the step from a CUDA graph (`denoise_step_graphed`, the
+    # pipeline's `cuda_graph` inference option) unless --graph 0; sharded steps are captured
+    # only with DWM_CUDA_GRAPH_SHARDED=1
+    use_graph = bool(args.graph) and (world == 1 or
+                                      os.environ.get("DWM_CUDA_GRAPH_SHARDED", "0") == "1")
+    e2e_step = pipe.denoise_step_graphed if use_graph else pipe.denoise_step
+
     def step_host(src_host, dst_host, idx_host, k):
         """End-to-end step: pinned host latents + indices in, updated latents out."""
         lat_dev.copy_(src_host, non_blocking=True)
         idx_dev.copy_(idx_host, non_blocking=True)
         _, ts, in_range = idx_list[k % 3]
-        pipe.denoise_step(lat_dev, cond, idx_dev, ts, in_range)
+        e2e_step(lat_dev, cond, idx_dev, ts, in_range)
         dst_host.copy_(lat_dev, non_blocking=True)
 
     def sync():
@@ -356,11 +363,13 @@ def run_native(args):
         "e2e": {"value": 1000.0 / ms_e2e, "unit": "steps/s",
                 "h2d_bytes_per_step": latents_host.numel() * 4 + idx_host[0].numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4,
-                "api": "StreamingCrossviewTemporalSD.denoise_step with pinned host "
+                "cuda_graph": use_graph,
+                "api": "StreamingCrossviewTemporalSD.denoise_step%s with pinned host "
                        "latents + index tensors copied in and latents copied out; a separate "
                        "timed loop (the device-resident loop above also records one CUDA-event "
                        "pair around each of its GEMM launches for the roofline, this one does "
-                       "not, which is why it can come out marginally faster)"},
+                       "not, which is why it can come out marginally faster)" %
+                       ("_graphed (CUDA-graph replay of the step)" if use_graph else "")},
         "gpu_launches": prof["launches"],
         "clocks": clocks,
     }
@@ -581,6 +590,9 @@ def run_reference(args):
 
 
 def main():
+    if os.environ.get("DWM_BENCH_WATCHDOG"):      # debugging aid: dump all stacks and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["DWM_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
@@ -593,6 +605,8 @@ def main():
                          "beside it (`other_dtype`)")
     ap.add_argument("--small", action="store_true", help="debug-size model/shape")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=1,
+                    help="1: the end-to-end loop replays the step from a CUDA graph")
     ap.add_argument("--cpu-budget", type=float, default=30.0)
     ap.add_argument("--no-extras", action="store_true",
                     help="skip streaming_e2e / workloads / eager_gpu_baseline / other dtype")

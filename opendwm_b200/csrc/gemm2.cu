@@ -130,26 +130,19 @@ __device__ __forceinline__ void rt_chunk_math(const uint32_t (&acc)[32], const R
   float4* row = reinterpret_cast<float4*>(rbuf) + lane * 8;
   const float4* xrow = xbuf ? reinterpret_cast<const float4*>(xbuf) + lane * 8 : nullptr;
   const float a1 = 1.0f - alpha;
-  const bool has_b = p.bias != nullptr, has_g = p.gate != nullptr;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int u = j ^ (lane & 7);
     float4 v = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
                            __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
-    if (has_b) {
-      const float4 b = vv.b[j];
-      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    }
-    if (has_g) {
-      const float4 g = vv.g[j];
-      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-    }
+    const float4 b = vv.b[j], g = vv.g[j];      // 0 / 1 when absent (rt_load_vecs)
     const float4 r = row[u];
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    v.x = resid_elem(v.x, b.x, g.x, r.x); v.y = resid_elem(v.y, b.y, g.y, r.y);
+    v.z = resid_elem(v.z, b.z, g.z, r.z); v.w = resid_elem(v.w, b.w, g.w, r.w);
     if (xrow) {
       const float4 x = xrow[u];
-      v.x = alpha * x.x + a1 * v.x; v.y = alpha * x.y + a1 * v.y;
-      v.z = alpha * x.z + a1 * v.z; v.w = alpha * x.w + a1 * v.w;
+      v.x = blend_elem(alpha, a1, x.x, v.x); v.y = blend_elem(alpha, a1, x.y, v.y);
+      v.z = blend_elem(alpha, a1, x.z, v.z); v.w = blend_elem(alpha, a1, x.w, v.w);
     }
     row[u] = v;
   }

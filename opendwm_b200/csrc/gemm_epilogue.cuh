@@ -47,6 +47,17 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// RESID arithmetic, spelled with explicit roundings so that every kernel variant (1-CTA /
+// 2-CTA, register / TMA-staged epilogue, convolution) produces the same bits whatever the
+// compiler would contract: v = fma(acc + bias, gate, resid); blend: fma(alpha, x, (1-alpha) v).
+// Absent bias / gate are 0 / 1, which leaves the value exact.
+__device__ __forceinline__ float resid_elem(float acc, float b, float g, float r) {
+  return __fmaf_rn(__fadd_rn(acc, b), g, r);
+}
+__device__ __forceinline__ float blend_elem(float a, float a1, float x, float v) {
+  return __fmaf_rn(a, x, __fmul_rn(a1, v));
+}
+
 __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c,
                                              uint32_t d) {
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d)
@@ -175,16 +186,15 @@ __device__ __forceinline__ void drain_tile(uint32_t taddr, float4* stg, int m_ba
       float4 v = stg[r * 8 + (c4 ^ (r & 7))];
       if (orow[it] >= 0) {
         if (EPI == DWM_EPI_RESID) {
-          v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          if (p.gate) {
-            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item[it]) * p.gate_ld + col));
-            v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-          }
-          v.x += rq[it].x; v.y += rq[it].y; v.z += rq[it].z; v.w += rq[it].w;
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (p.gate)
+            g = __ldg(reinterpret_cast<const float4*>(p.gate + static_cast<long long>(item[it]) * p.gate_ld + col));
+          v.x = resid_elem(v.x, b.x, g.x, rq[it].x); v.y = resid_elem(v.y, b.y, g.y, rq[it].y);
+          v.z = resid_elem(v.z, b.z, g.z, rq[it].z); v.w = resid_elem(v.w, b.w, g.w, rq[it].w);
           if (p.blend_x) {
             const float a = alpha[it], a1 = 1.0f - alpha[it];
-            v.x = a * bq[it].x + a1 * v.x; v.y = a * bq[it].y + a1 * v.y;
-            v.z = a * bq[it].z + a1 * v.z; v.w = a * bq[it].w + a1 * v.w;
+            v.x = blend_elem(a, a1, bq[it].x, v.x); v.y = blend_elem(a, a1, bq[it].y, v.y);
+            v.z = blend_elem(a, a1, bq[it].z, v.z); v.w = blend_elem(a, a1, bq[it].w, v.w);
           }
         }
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow[it]) * p.ldo + col) = v;

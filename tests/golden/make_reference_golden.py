@@ -41,8 +41,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/src"
-# order matters: the reference's `dwm`, not this repo's src/dwm mirror
-sys.path[:0] = [REF, os.path.join(HERE, "diffusers_stub"), ROOT, os.path.join(ROOT, "tests")]
+# order matters: the reference's `dwm`, not this repo's src/dwm mirror.  With
+# DWM_REAL_DIFFUSERS=1 (tools/pin_diffusers.py) the name shim is left out and the reference runs
+# on the real `diffusers` package; DWM_GOLDEN_OUT redirects the output files.
+REAL = os.environ.get("DWM_REAL_DIFFUSERS", "0") == "1"
+OUT = os.environ.get("DWM_GOLDEN_OUT", HERE)
+sys.path[:0] = [REF] + ([] if REAL else [os.path.join(HERE, "diffusers_stub")]) + \
+    [ROOT, os.path.join(ROOT, "tests")]
 
 import torch  # noqa: E402
 
@@ -245,15 +250,16 @@ def main():
         ref_pipe.CrossviewTemporalSD,
         (diffusers.SD3Transformer2DModel, diffusers.UNetSpatioTemporalConditionModel), name, stack)
         for name in TEXT_CASES}
-    with open(os.path.join(HERE, "reference_text_conditions.json"), "w") as f:
+    with open(os.path.join(OUT, "reference_text_conditions.json"), "w") as f:
         json.dump(text, f, indent=1)
 
-    safetensors.torch.save_file(out, os.path.join(HERE, "reference_outputs.safetensors"))
-    with open(os.path.join(HERE, "reference_autoregressive_traces.json"), "w") as f:
+    safetensors.torch.save_file(out, os.path.join(OUT, "reference_outputs.safetensors"))
+    with open(os.path.join(OUT, "reference_autoregressive_traces.json"), "w") as f:
         json.dump(traces, f, indent=1)
-    with open(os.path.join(HERE, "reference_outputs.json"), "w") as f:
-        json.dump({"generated_from": "/root/reference/src (OpenDWM @ b0ecc3d) on the "
-                                     "diffusers shim tests/golden/diffusers_stub",
+    with open(os.path.join(OUT, "reference_outputs.json"), "w") as f:
+        json.dump({"generated_from": "/root/reference/src (OpenDWM @ b0ecc3d) on " +
+                                     ("the real diffusers package" if REAL else
+                                      "the diffusers shim tests/golden/diffusers_stub"),
                    "torch": torch.__version__, "cases": report}, f, indent=1)
     for k, v in report.items():
         print(k, v)
