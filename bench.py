@@ -294,7 +294,7 @@ def run_native(args):
         ms_e2e = t.item()
 
     if rank != 0:
-        torch.distributed.destroy_process_group()
+        _leave(world)
         return
     frame_latency = None
     if world == 1 and not args.small:
@@ -424,9 +424,27 @@ def run_native(args):
             line["other_dtype"] = {"dtype": other, "error": repr(e)[:300]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(budget_s=args.cpu_budget, small=args.small)
-    print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _leave(world):
+    """Multi-rank exit.  `destroy_process_group` was observed to hang on this pool after runs
+    that used symmetric-memory handles / captured NCCL work (8 GPUs, r02: every rank sat in it
+    until the watchdog fired, AFTER the result line had been printed), which would turn a good
+    measurement into a timed-out run.  The result is out and nothing needs flushing, so the
+    ranks synchronise and leave without tearing NCCL down."""
+    if world <= 1:
+        return
+    try:
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def decode_latency(dev, dtype, V, C, H, W, ms_step):

@@ -8,7 +8,7 @@
 //
 // Used by: CogVideoX causal conv3d (3x3x3), its per-frame upsampler conv2d (1x3x3), and
 // the T2I-adapter 3x3 convs.  Epilogues are the GEMM ones (bias/act store, fp32 residual).
-#include "gemm_epilogue.cuh"
+#include "cta_pair.cuh"
 
 namespace dwm {
 
@@ -152,6 +152,158 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// cta_group::2 variant: a cluster of two CTAs computes TWO pixel tiles (M = 256) x CBN output
+// channels.  Each CTA stages its own shifted pixel patch (A, 128 rows) and HALF of the tap's
+// weight slice, so per MMA step an SM reads 4 KB + CBN/2 x 32 B of shared memory: at
+// C_out = 128 that is 96 B/clk instead of the 128 B/clk that made the 1-CTA kernel shared-
+// memory bound (tensor pipe 47 %, profiles/r01_ncu_kernels_summary.txt); at C_out = 256 it is
+// 64 instead of 96 B/clk (less energy per FLOP).  Protocol = gemm2.cu.  An odd tile count gives
+// the last pair a dummy second tile: its loads are out of bounds (zero fill) and its rows are
+// never stored.
+constexpr int CV2_STAGES = 5;
+
+template <typename T, int EPI, int CBN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    conv2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const ConvGeom g, EpiParams p) {
+  constexpr int B_BYTES = (CBN / 2) * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + CV2_STAGES * CV_A_BYTES;
+  float4* epi_stage = reinterpret_cast<float4*>(smem + CV2_STAGES * (CV_A_BYTES + B_BYTES));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CV2_STAGES * (CV_A_BYTES + B_BYTES) + EPI_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + CV2_STAGES;
+  uint64_t* tfull_bar = bars + 2 * CV2_STAGES;
+  uint64_t* tempty_bar = bars + 2 * CV2_STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * CV2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int n_blocks = (g.c_out + CBN - 1) / CBN;
+  const int c_blocks = (g.c_in + BK - 1) / BK;
+  const int taps = g.kt * g.kh * g.kw;
+  const int k_iters = taps * c_blocks;
+  const long long m_tiles = static_cast<long long>(g.nb) * g.t_out * g.tiles_w * g.tiles_h;
+  const long long pairs = (m_tiles + 1) / 2;
+  const long long num_tiles = pairs * n_blocks;
+  // both CTAs' loads complete on the leader's barrier: 2 x (pixel patch + weight half)
+  const uint32_t stage_tx = 2u * static_cast<uint32_t>(g.bw * g.bh * BK * 2 + B_BYTES);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < CV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // pair tile -> (n_blk fastest, then the pair of pixel tiles); this CTA's pixel tile
+  auto decode = [&](long long tile, int& n_blk, int& w0, int& h0, int& t, int& nb) -> bool {
+    n_blk = static_cast<int>(tile % n_blocks);
+    long long r = (tile / n_blocks) * 2 + rank;
+    const bool valid = r < m_tiles;
+    w0 = static_cast<int>(r % g.tiles_w) * g.bw; r /= g.tiles_w;
+    h0 = static_cast<int>(r % g.tiles_h) * g.bh; r /= g.tiles_h;
+    t = static_cast<int>(r % g.t_out);
+    nb = static_cast<int>(r / g.t_out);      // == g.nb for the dummy tile: out of bounds, zero fill
+    return valid;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        int n_blk, w0, h0, t, nb;
+        decode(tile, n_blk, w0, h0, t, nb);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dw = tap % g.kw, dh = (tap / g.kw) % g.kh, dt = tap / (g.kw * g.kh);
+          for (int cb = 0; cb < c_blocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_5d_2sm(&tmap_x, leader_full, smem_a + stage * CV_A_BYTES, cb * BK, w0 + dw - g.kw / 2,
+                            h0 + dh - g.kh / 2, t + dt, nb, kEvictNormal);
+            tma_load_2d_2sm(&tmap_w, leader_full, smem_b + stage * B_BYTES, cb * BK,
+                            tap * g.c_out + n_blk * CBN + static_cast<int>(rank) * (CBN / 2), kEvictLast);
+            if (++stage == CV2_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(2 * BM, CBN, Cvt<T>::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * CBN;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * CV_A_BYTES));
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | k) ? 1u : 0u);
+          umma_commit_2sm_mc(&empty_bar[stage]);
+          if (++stage == CV2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_mc(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    int it = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      int n_blk, w0, h0, t, nb;
+      const bool valid = decode(tile, n_blk, w0, h0, t, nb);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      if (valid) {
+        const uint32_t taddr = tmem_base + as * CBN + (static_cast<uint32_t>(quarter * 32) << 16);
+        TileGeom tg;
+        tg.bw = g.bw; tg.rows = g.bw * g.bh; tg.w_lim = g.w - w0; tg.h_lim = g.h - h0; tg.img_w = g.w;
+        tg.tile_cols = CBN;
+        const int m_base = ((nb * g.t_out + t) * g.h + h0) * g.w + w0;
+        drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256, m_base, quarter * 32, 0, n_blk * CBN, g.c_out, p,
+                           lane, (warp - 2) >> 2, tg);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+int g_conv_2cta = -1;   // -1: env DWM_CONV_2CTA (default 1); dwm_b200_set_option("conv_2cta", 0 | 1)
+
 int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, int elem_bytes);   // host.cu
 
@@ -192,6 +344,36 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
   p.norm_regions = 2;
   p.n_peers = 0;
 
+  const long long n_blocks = (g.c_out + CBN - 1) / CBN;
+  const long long tiles = static_cast<long long>(g.nb) * g.t_out * g.tiles_w * g.tiles_h * n_blocks;
+  const int sms = sm_count();
+  if (g_conv_2cta < 0) {
+    const char* e = getenv("DWM_CONV_2CTA");
+    g_conv_2cta = (e && e[0] == '0') ? 0 : 1;
+  }
+  // cta_group::2 pairs once there are enough pixel tiles to fill the SM pairs (CBN >= 64: the
+  // W half of a pair must be a whole 8-row swizzle atom per CTA)
+  if constexpr (CBN >= 64) {
+    if (g_conv_2cta == 1 && tiles >= 2 * sms) {
+      // weight box = half of the CBN rows
+      rc = make_tmap_2d(&tw, a->weight, static_cast<uint64_t>(taps) * a->c_out, a->c_in, a->c_in, CBN / 2, BK, 2);
+      if (rc) return rc;
+      auto kern2 = conv2_tcgen05_kernel<T, EPI, CBN>;
+      constexpr int smem2 = CV2_STAGES * (CV_A_BYTES + (CBN / 2) * BK * 2) + EPI_STAGE_BYTES + 1024 + 256;
+      static bool attr2_set = false;
+      if (!attr2_set) {
+        DWM_CHECK_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        attr2_set = true;
+      }
+      const long long m_tiles = tiles / n_blocks;
+      const long long ptiles = ((m_tiles + 1) / 2) * n_blocks;
+      const int pairs = sms / 2;
+      const int clusters = static_cast<int>(ptiles < pairs ? ptiles : pairs);
+      kern2<<<2 * clusters, GEMM_THREADS, smem2, stream>>>(tx, tw, g, p);
+      DWM_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   auto kern = conv_tcgen05_kernel<T, EPI, CBN>;
   constexpr int smem_bytes = CV_STAGES * (CV_A_BYTES + CBN * BK * 2) + EPI_STAGE_BYTES + 1024 + 256;
   static bool attr_set = false;
@@ -199,9 +381,6 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
     DWM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_set = true;
   }
-  const long long n_blocks = (g.c_out + CBN - 1) / CBN;
-  const long long tiles = static_cast<long long>(g.nb) * g.t_out * g.tiles_w * g.tiles_h * n_blocks;
-  const int sms = sm_count();
   const int grid = static_cast<int>(tiles < sms ? tiles : sms);
   kern<<<grid, GEMM_THREADS, smem_bytes, stream>>>(tx, tw, g, p);
   DWM_CHECK_CUDA(cudaGetLastError());

@@ -10,7 +10,7 @@
 //   empty[s]   both CTAs; the leader's MMA thread commits with a cluster multicast
 //   tfull[a]   both CTAs (multicast commit) -> each CTA drains its own 128 TMEM lanes
 //   tempty[a]  leader only; all 16 epilogue warps of the pair arrive (remote arrive)
-#include "gemm_epilogue.cuh"
+#include "cta_pair.cuh"
 
 namespace dwm {
 
@@ -31,64 +31,6 @@ template <bool RT, int BNT> struct G2Cfg {
   static constexpr int kEpiBytes = RT ? RT_EPI_BYTES : EPI_STAGE_BYTES;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 512;
 };
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint32_t bar_cluster_addr,
-                                                void* smem, int32_t c0, int32_t c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :
-      : "r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
-        "l"(hint)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n"
-      :
-      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit to the same barrier offset in both CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar) {
-  const uint16_t mask = 3;
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"(mask)
-      : "memory");
-}
 
 // ---- bulk-tensor store (shared -> global) and its group bookkeeping ------------------------
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem, int32_t c0, int32_t c1) {
@@ -413,15 +355,24 @@ static double wave_eff(long long tiles, int pairs) {
   return static_cast<double>(tiles) / static_cast<double>(waves * pairs);
 }
 // 128-column tiles cost ~50 % more shared-memory operand traffic per FLOP and twice the
-// per-tile bookkeeping, so they are used only where they repair a tail wave by > 6 %.
+// per-tile bookkeeping: measured on B200 (tools/shard_emulate.py 8, r02) they LOSE 5 % at
+// M = 10 752 (wave efficiency 0.85 -> 0.97: 183 vs 173 us for N = 1536, K = 6144) and WIN 8 % at
+// M = 3 696 (0.61 -> 0.81: 85 vs 92 us), so they are used only where they repair the tail
+// wave by more than 15 points.
 static bool narrow_tiles_pay(const dwm_linear_args* a) {
+  static bool env_read = false;
+  if (!env_read) {               // DWM_GEMM_BN = 128 | 256 forces a tile width (measurement aid)
+    env_read = true;
+    const char* e = getenv("DWM_GEMM_BN");
+    if (e && g_gemm_bn == 0) g_gemm_bn = atoi(e);
+  }
   if (g_gemm_bn == 128) return true;
   if (g_gemm_bn == 256) return false;
   const int pairs = sm_count() / 2;
   const long long mb = (a->M + 2 * BM - 1) / (2 * BM);
   const double e256 = wave_eff(mb * ((a->N + 255) / 256), pairs);
   const double e128 = wave_eff(mb * ((a->N + 127) / 128), pairs);
-  return e128 > e256 + 0.06;
+  return e128 > e256 + 0.15;
 }
 
 template <typename T, int EPI, bool RT, int BNT>

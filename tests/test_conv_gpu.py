@@ -4,6 +4,7 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+_LAST = [None]      # output of the most recent _case (kernel-variant comparisons)
 
 
 def _case(nb, t_out, h, w, cin, cout, kernel, dtype, epilogue="f32", seed=0):
@@ -31,6 +32,7 @@ def _case(nb, t_out, h, w, cin, cout, kernel, dtype, epilogue="f32", seed=0):
     else:
         y = ops.conv(xcl, wp, bp, kernel=kernel, epilogue=lib.EPI_STORE, act=lib.ACT_SILU)[:, :cout].float()
         ref = torch.nn.functional.silu(ref)
+    _LAST[0] = y
     return ((y - ref).abs().max() / ref.abs().max()).item()
 
 
@@ -76,3 +78,29 @@ def test_per_item_residual():
     ref = ref + temb[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1).reshape(-1, cout)
     assert ((y - ref).abs().max() / ref.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("epilogue", ["f32", "resid", "store"])
+@pytest.mark.parametrize("shape", [
+    (2, 3, 64, 96, 64, 128, (3, 3, 3)),     # 384 pixel tiles: C_out 128 (the smem-bound width)
+    (1, 2, 150, 128, 64, 256, (1, 3, 3)),   # 300 tiles, C_out 256
+    (3, 1, 101, 120, 72, 64, (1, 3, 3)),    # 303 tiles (odd: dummy last tile), C_out 64
+    (1, 1, 299, 130, 128, 320, (1, 3, 3)),  # ragged W tiles, 5 N tiles of 64
+])
+def test_two_cta_conv_equals_one_cta(shape, epilogue):
+    """Enough pixel tiles (>= 2 x SMs) route the convolution to the cta_group::2 kernel (two
+    pixel tiles per MMA, half a weight slice per CTA); it must agree with the 1-CTA kernel bit
+    for bit (same accumulation order) and with torch."""
+    from opendwm_b200 import lib
+    lib.set_option("conv_2cta", 1)
+    try:
+        e2 = _case(*shape, torch.float16, epilogue, seed=3)
+        y2 = _LAST[0].clone()
+        lib.set_option("conv_2cta", 0)
+        e1 = _case(*shape, torch.float16, epilogue, seed=3)
+        y1 = _LAST[0]
+    finally:
+        lib.set_option("conv_2cta", 1)
+    assert e2 < (8e-3 if epilogue == "store" else 1e-3), e2
+    assert e1 < (8e-3 if epilogue == "store" else 1e-3), e1
+    assert torch.equal(y1, y2)
