@@ -234,8 +234,9 @@ def run_native(args):
     # the end-to-end loop replays the step from a CUDA graph (`denoise_step_graphed`, the
     # pipeline's `cuda_graph` inference option) unless --graph 0; sharded steps are captured
     # only with DWM_CUDA_GRAPH_SHARDED=1
+    os.environ.setdefault("DWM_CUDA_GRAPH_SHARDED", "1")   # measured on 8 GPUs (r02): captures
     use_graph = bool(args.graph) and (world == 1 or
-                                      os.environ.get("DWM_CUDA_GRAPH_SHARDED", "0") == "1")
+                                      os.environ["DWM_CUDA_GRAPH_SHARDED"] == "1")
     e2e_step = pipe.denoise_step_graphed if use_graph else pipe.denoise_step
 
     def step_host(src_host, dst_host, idx_host, k):

@@ -139,9 +139,17 @@ struct SnParams {
 // instead of per thread — the fp64 divisions made the per-thread version XU-pipe bound.
 constexpr int SN_CHUNK = 4096;
 
+// Per-thread state is set up ONCE: with blockDim a multiple of C/4 a thread keeps the same
+// channel quad for all its elements, so gamma / beta / (mean, rstd) are registers, the pixel
+// position (t, h, w) advances by a constant number of pixels per iteration and is tracked with
+// carries instead of 64-bit divisions, the latent-grid coordinates are shifts when the sizes
+// are powers of two apart (always in the VAEs) and the frame map is a 64-entry shared table.
+// The r01 kernel spent ~10 integer divisions per float4 and ran at 18 % of DRAM peak
+// (profiles/r01_ncu_kernels_summary.txt); this one is a plain stream.
 template <typename T>
 __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
   __shared__ float2 s_stat[64];
+  __shared__ int s_tz[64];
   const int vec = p.C >> 2;
   const int n = blockIdx.y;
   const int cg = p.C / p.G;
@@ -154,11 +162,67 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
     s_stat[threadIdx.x] = make_float2(static_cast<float>(mean_d),
                                       rsqrtf(static_cast<float>(ss / cnt - mean_d * mean_d) + p.eps));
   }
+  if (p.zy && threadIdx.x < 64 && threadIdx.x < p.T) {
+    // nearest-neighbour frame of the latent grid; odd T > 1 treats the first frame apart
+    const int t = threadIdx.x;
+    s_tz[t] = (p.T > 1 && (p.T & 1)) ? (t == 0 ? 0 : 1 + ((t - 1) * (p.Tz - 1)) / (p.T - 1))
+                                     : (t * p.Tz) / p.T;
+  }
   __syncthreads();
   const long long i0 = static_cast<long long>(blockIdx.x) * SN_CHUNK;
   long long i1 = i0 + SN_CHUNK;
   if (i1 > per_img) i1 = per_img;
   const float4* xin = reinterpret_cast<const float4*>(p.x) + static_cast<long long>(n) * per_img;
+  const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(p.beta);
+  const bool fast = (256 % vec) == 0 && (SN_CHUNK % vec) == 0 && (cg & 3) == 0 && p.T <= 64;
+  if (fast) {
+    const int c4 = threadIdx.x % vec;
+    const int pstep = 256 / vec;                                  // pixels per iteration
+    long long pix = i0 / vec + threadIdx.x / vec;                 // i0 % vec == 0
+    int w = static_cast<int>(pix % p.W);
+    long long r = pix / p.W;
+    int h = static_cast<int>(r % p.H);
+    int t = static_cast<int>(r / p.H);
+    const float4 ga = __ldg(g4 + c4), be = __ldg(b4 + c4);
+    const float2 st = s_stat[(c4 * 4) / cg];
+    // (x - mean) * (rstd * gamma) + beta: the subtraction stays first (no cancellation in a
+    // pre-folded offset when |mean| >> std)
+    const float4 aa = make_float4(st.y * ga.x, st.y * ga.y, st.y * ga.z, st.y * ga.w);
+    const float mu = st.x;
+    // latent-grid coordinates: shifts when H = hz << k (else a division per element)
+    int hs = -1, ws = -1;
+    if (p.zy) {
+      for (int k = 0; k < 8; ++k) {
+        if ((p.hz << k) == p.H) hs = k;
+        if ((p.wz << k) == p.W) ws = k;
+      }
+    }
+    const long long zn = static_cast<long long>(n) * p.Tz;
+    const long long on = static_cast<long long>(n) * p.out_T + p.out_t0;
+    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+      float4 v = xin[i];
+      v.x = fmaf(v.x - mu, aa.x, be.x); v.y = fmaf(v.y - mu, aa.y, be.y);
+      v.z = fmaf(v.z - mu, aa.z, be.z); v.w = fmaf(v.w - mu, aa.w, be.w);
+      if (p.zy) {
+        const int hq = hs >= 0 ? (h >> hs) : (h * p.hz) / p.H;
+        const int wq = ws >= 0 ? (w >> ws) : (w * p.wz) / p.W;
+        const long long zi = (((zn + s_tz[t]) * p.hz + hq) * p.wz + wq) * vec + c4;
+        const float4 y = __ldg(reinterpret_cast<const float4*>(p.zy) + zi);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.zb) + zi);
+        v.x = fmaf(v.x, y.x, b.x); v.y = fmaf(v.y, y.y, b.y);
+        v.z = fmaf(v.z, y.z, b.z); v.w = fmaf(v.w, y.w, b.w);
+      }
+      if (p.silu) { v.x = silu(v.x); v.y = silu(v.y); v.z = silu(v.z); v.w = silu(v.w); }
+      const long long o = (((on + t) * p.H + h) * p.W + w) * vec + c4;
+      uint2 pk; pk.x = Cvt<T>::pack2(v.x, v.y); pk.y = Cvt<T>::pack2(v.z, v.w);
+      reinterpret_cast<uint2*>(p.out)[o] = pk;
+      w += pstep;
+      while (w >= p.W) { w -= p.W; if (++h == p.H) { h = 0; ++t; } }
+    }
+    return;
+  }
+  // general path: any channel count / group size (UNet widths 320 / 640 / 1280 ...)
   for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
     const int c4 = static_cast<int>(i % vec);
     long long r = i / vec;
@@ -166,8 +230,8 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
     const int h = static_cast<int>(r % p.H);
     const int t = static_cast<int>(r / p.H);
     float4 v = xin[i];
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
-    const float4 be = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+    const float4 ga = __ldg(g4 + c4);
+    const float4 be = __ldg(b4 + c4);
     if ((cg & 3) == 0) {
       const float2 st = s_stat[(c4 * 4) / cg];
       v.x = (v.x - st.x) * st.y * ga.x + be.x;
@@ -185,7 +249,6 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
       }
     }
     if (p.zy) {
-      // nearest-neighbour position in the latent grid; odd T > 1 treats the first frame apart
       int tz;
       if (p.T > 1 && (p.T & 1)) tz = t == 0 ? 0 : 1 + ((t - 1) * (p.Tz - 1)) / (p.T - 1);
       else tz = (t * p.Tz) / p.T;

@@ -251,7 +251,10 @@ class AutoencoderKLCogVideoX(torch.nn.Module):
             x_pad[:, :2].copy_(prev)
         else:
             x_pad[:, :2].copy_(x_pad[:, 2:3].expand(-1, 2, -1, -1, -1))
-        new_cache[name] = x_pad[:, -2:].clone()
+        # the cached tail is a VIEW of this chunk's padded input (every x_pad is a fresh buffer
+        # that nothing writes again), copied once into the next chunk's padding: one copy per
+        # convolution and chunk instead of clone + copy
+        new_cache[name] = x_pad[:, -2:]
         return _ops.conv(x_pad, wb[0], wb[1], kernel=(3, 3, 3), **kw)
 
     def _norm_act(self, h, shape, p, zq16, zshape, groups):

@@ -16,7 +16,9 @@ def main(path, out=None, delim="patchify", detail=False):
     # delim "x": a step starts at each kernel whose name contains x; "end:x": ends at it
     end = delim.startswith("end:")
     key = delim[4:] if end else delim
-    starts = [i + (1 if end else 0) for i, (n, _, _) in enumerate(names) if key in n]
+    # (a run of consecutive delimiter kernels — the CFG-doubled step patchifies twice — is one mark)
+    starts = [i + (1 if end else 0) for i, (n, _, _) in enumerate(names)
+              if key in n and (end or i == 0 or key not in names[i - 1][0])]
     a, b = starts[-2], starts[-1]
     step = names[a:b]
     agg = collections.defaultdict(lambda: [0, 0.0])
