@@ -65,6 +65,11 @@ def main():
     w_ff1 = (rnd(4 * D, D) * 0.02).to(dt)
     todo.append(("GEMM FF1 86016x6144x1536 STORE+GELU", lambda: ops.linear(
         a16, w_ff1, None, act=lib.ACT_GELU_TANH, out=g16)))
+    # the step's dominant kernel: VT-block FF1 with the GEGLU epilogue (packed 8D x D weight)
+    w_gg, b_gg = ops.pack_geglu(rnd(8 * D, D) * 0.02, torch.zeros(8 * D, device=dev))
+    w_gg = w_gg.to(dt)
+    todo.append(("GEMM GEGLU 86016x12288x1536 (dominant)", lambda: ops.linear(
+        a16, w_gg, b_gg, epilogue=lib.EPI_GEGLU, out=g16)))
 
     # --- convolution / GroupNorm (VAE shapes) ----------------------------------------------
     xc = rnd(2, 2 + 2, 128, 224, 256).to(dt)                  # CogVideoX up-block, 256 ch
