@@ -302,6 +302,176 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Halo-row variant of the cta_group::2 kernel for kw = 3 and W >= 128.  The kernels above
+// re-read the shifted activation patch from L2 once per TAP: at C_out = 128 that is 94 B/clk/SM
+// of L2->SM operand traffic and the measured limiter (tensor pipe 47 %).  Here
+// an M tile is ONE image-row segment of 128 pixels; per (dt, dh, C_in block) the producer loads
+// the segment with a one-pixel halo on both sides ONCE (130 rows x 128 B, TMA zero fill = the
+// spatial padding) plus the three weight slices of dw = 0, 1, 2, and the MMA warp issues the three
+// taps against ROW-SHIFTED views of that one shared-memory tile: the UMMA descriptor simply
+// starts dw rows (dw x 128 B) into the tile.  Measured on B200 (tools/conv_halo_probe.py, r02):
+// the 128-byte swizzle phase follows the ABSOLUTE shared-memory address bits [7:9], exactly as
+// TMA wrote the tile, so a start address that is not aligned to the 1024-byte pattern needs NO
+// base-offset field (bits 49-51 = 0 is exact to 1e-6 against torch; = dw gives garbage).  A
+// traffic drops 3x (27 -> 9 loads per C_in block for 3x3x3).
+constexpr int CVH_A_ROWS = 130;
+constexpr int CVH_A_BYTES = 17 * 1024;        // 130 rows x 128 B, rounded up to the swizzle pattern
+
+template <int CBN> struct CvhCfg {
+  static constexpr int kBBytes = (CBN / 2) * BK * 2;               // one tap's weight half
+  static constexpr int kStageBytes = CVH_A_BYTES + 3 * kBBytes;
+  static constexpr int kStages = 4;            // CBN <= 128: 4 x <= 41 KB
+  static constexpr int kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024 + 256;
+};
+
+int g_conv_halo = -1;         // -1: env DWM_CONV_HALO (default 1); option "conv_halo"
+
+template <typename T, int EPI, int CBN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    convh_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                         const ConvGeom g, EpiParams p) {
+  using Cfg = CvhCfg<CBN>;
+  constexpr int B_BYTES = Cfg::kBBytes;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float4* epi_stage = reinterpret_cast<float4*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes + EPI_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+  const int n_blocks = (g.c_out + CBN - 1) / CBN;
+  const int c_blocks = (g.c_in + BK - 1) / BK;
+  const int outer_taps = g.kt * g.kh;                       // (dt, dh); dw runs inside the stage
+  const int k_iters = outer_taps * c_blocks;
+  const int w_tiles = (g.w + 127) / 128;
+  const long long m_tiles = static_cast<long long>(g.nb) * g.t_out * g.h * w_tiles;
+  const long long pairs = (m_tiles + 1) / 2;
+  const long long num_tiles = pairs * n_blocks;
+  const uint32_t stage_tx = 2u * static_cast<uint32_t>(CVH_A_ROWS * BK * 2 + 3 * B_BYTES);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // pair tile -> (n_blk fastest, then the pair of row segments); this CTA's segment
+  auto decode = [&](long long tile, int& n_blk, int& w0, int& h, int& t, int& nb) -> bool {
+    n_blk = static_cast<int>(tile % n_blocks);
+    long long r = (tile / n_blocks) * 2 + rank;
+    const bool valid = r < m_tiles;
+    w0 = static_cast<int>(r % w_tiles) * 128; r /= w_tiles;
+    h = static_cast<int>(r % g.h); r /= g.h;
+    t = static_cast<int>(r % g.t_out);
+    nb = static_cast<int>(r / g.t_out);      // == g.nb for the dummy tile: out of bounds, zero fill
+    return valid;
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        int n_blk, w0, h, t, nb;
+        decode(tile, n_blk, w0, h, t, nb);
+        for (int ot = 0; ot < outer_taps; ++ot) {
+          const int dh = ot % g.kh, dt = ot / g.kh;
+          for (int cb = 0; cb < c_blocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_5d_2sm(&tmap_x, leader_full, st, cb * BK, w0 - 1, h + dh - g.kh / 2, t + dt, nb, kEvictNormal);
+#pragma unroll
+            for (int dw = 0; dw < 3; ++dw)
+              tma_load_2d_2sm(&tmap_w, leader_full, st + CVH_A_BYTES + dw * B_BYTES, cb * BK,
+                              (ot * 3 + dw) * g.c_out + n_blk * CBN + static_cast<int>(rank) * (CBN / 2), kEvictLast);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(2 * BM, CBN, Cvt<T>::kUmmaFmt);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * CBN;
+        for (int ki = 0; ki < k_iters; ++ki) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * Cfg::kStageBytes);
+#pragma unroll
+          for (int dw = 0; dw < 3; ++dw) {
+            const uint64_t da = umma_desc_sw128(st + dw * 128u);       // row-shifted view
+            const uint64_t db = umma_desc_sw128(st + CVH_A_BYTES + dw * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (ki | dw | k) ? 1u : 0u);
+          }
+          umma_commit_2sm_mc(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm_mc(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    int it = 0;
+    for (long long tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      int n_blk, w0, h, t, nb;
+      const bool valid = decode(tile, n_blk, w0, h, t, nb);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      if (valid) {
+        const uint32_t taddr = tmem_base + as * CBN + (static_cast<uint32_t>(quarter * 32) << 16);
+        TileGeom tg;
+        tg.bw = 128; tg.rows = 128; tg.w_lim = g.w - w0; tg.h_lim = 1; tg.img_w = g.w;
+        tg.tile_cols = CBN;
+        const int m_base = ((nb * g.t_out + t) * g.h + h) * g.w + w0;
+        drain_tile<T, EPI>(taddr, epi_stage + (warp - 2) * 256, m_base, quarter * 32, 0, n_blk * CBN, g.c_out, p,
+                           lane, (warp - 2) >> 2, tg);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(mapa_u32(smem_u32(&tempty_bar[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 int g_conv_2cta = -1;   // -1: env DWM_CONV_2CTA (default 1); dwm_b200_set_option("conv_2cta", 0 | 1)
 
 int make_tmap_nd(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -354,6 +524,35 @@ static int launch_conv(const dwm_conv_args* a, cudaStream_t stream) {
   // cta_group::2 pairs once there are enough pixel tiles to fill the SM pairs (CBN >= 64: the
   // W half of a pair must be a whole 8-row swizzle atom per CTA)
   if constexpr (CBN >= 64) {
+    if (g_conv_halo < 0) {
+      const char* e = getenv("DWM_CONV_HALO");
+      g_conv_halo = (e && e[0] == '0') ? 0 : 1;
+    }
+    // halo-row kernel: kw = 3, rows of at least 128 pixels, enough row segments for the pairs
+    const long long seg_tiles = static_cast<long long>(g.nb) * g.t_out * g.h * ((g.w + 127) / 128) * n_blocks;
+    // (C_out tiles of 256 columns are MMA-bound already — 94 % tensor pipe — and their three
+    // weight slices per stage would not fit)
+    if (CBN <= 128 && g_conv_2cta == 1 && g_conv_halo == 1 && a->kw == 3 && g.w >= 128 && seg_tiles >= 2 * sms) {
+      using Cfg = CvhCfg<(CBN <= 128 ? CBN : 128)>;
+      CUtensorMap txh;
+      const uint32_t boxh[5] = {BK, static_cast<uint32_t>(CVH_A_ROWS), 1, 1, 1};
+      rc = make_tmap_nd(&txh, a->x, 5, dims, st, boxh, 2);
+      if (rc) return rc;
+      rc = make_tmap_2d(&tw, a->weight, static_cast<uint64_t>(taps) * a->c_out, a->c_in, a->c_in, CBN / 2, BK, 2);
+      if (rc) return rc;
+      auto kernh = convh_tcgen05_kernel<T, EPI, (CBN <= 128 ? CBN : 128)>;
+      static bool attrh_set = false;
+      if (!attrh_set) {
+        DWM_CHECK_CUDA(cudaFuncSetAttribute(kernh, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attrh_set = true;
+      }
+      const long long ptiles = ((seg_tiles / n_blocks + 1) / 2) * n_blocks;
+      const int pairs = sms / 2;
+      const int clusters = static_cast<int>(ptiles < pairs ? ptiles : pairs);
+      kernh<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(txh, tw, g, p);
+      DWM_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
     if (g_conv_2cta == 1 && tiles >= 2 * sms) {
       // weight box = half of the CBN rows
       rc = make_tmap_2d(&tw, a->weight, static_cast<uint64_t>(taps) * a->c_out, a->c_in, a->c_in, CBN / 2, BK, 2);

@@ -205,7 +205,7 @@ int g_gemm_2cta = -1;   // -1: from env DWM_GEMM_2CTA (default 1), 0 / 1: forced
 
 }  // namespace dwm
 
-namespace dwm { int g_attn_tc = -1; extern int g_ln_staged; extern int g_resid_tma; extern int g_gemm_bn; extern int g_conv_2cta; }
+namespace dwm { int g_attn_tc = -1; extern int g_ln_staged; extern int g_resid_tma; extern int g_gemm_bn; extern int g_conv_2cta; extern int g_conv_halo; }
 
 extern "C" int dwm_b200_set_option(const char* name, int value) {
   using namespace dwm;
@@ -216,6 +216,7 @@ extern "C" int dwm_b200_set_option(const char* name, int value) {
   if (strcmp(name, "resid_tma") == 0) { g_resid_tma = value; return 0; }
   if (strcmp(name, "gemm_bn") == 0) { g_gemm_bn = value; return 0; }
   if (strcmp(name, "conv_2cta") == 0) { g_conv_2cta = value; return 0; }
+  if (strcmp(name, "conv_halo") == 0) { g_conv_halo = value; return 0; }
   set_last_error("dwm_b200_set_option: unknown option %s", name);
   return -1;
 }

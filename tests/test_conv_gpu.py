@@ -93,6 +93,7 @@ def test_two_cta_conv_equals_one_cta(shape, epilogue):
     for bit (same accumulation order) and with torch."""
     from opendwm_b200 import lib
     lib.set_option("conv_2cta", 1)
+    lib.set_option("conv_halo", 0)       # the per-tap pair kernel, not the halo-row one
     try:
         e2 = _case(*shape, torch.float16, epilogue, seed=3)
         y2 = _LAST[0].clone()
@@ -101,6 +102,33 @@ def test_two_cta_conv_equals_one_cta(shape, epilogue):
         y1 = _LAST[0]
     finally:
         lib.set_option("conv_2cta", 1)
+        lib.set_option("conv_halo", 1)
     assert e2 < (8e-3 if epilogue == "store" else 1e-3), e2
     assert e1 < (8e-3 if epilogue == "store" else 1e-3), e1
     assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("epilogue", ["f32", "resid", "store"])
+@pytest.mark.parametrize("shape", [
+    (2, 1, 160, 200, 64, 128, (1, 3, 3)),    # W = 200: one full + one ragged 72-pixel segment
+    (1, 3, 64, 130, 128, 128, (3, 3, 3)),    # causal 3x3x3, second segment holds 2 pixels
+    (1, 1, 300, 128, 72, 64, (1, 3, 3)),     # C_out 64, partial second C_in block
+    (3, 1, 101, 448, 128, 128, (1, 3, 3)),   # VAE width 448 (3.5 segments), odd tile count
+])
+def test_halo_row_conv_equals_shifted_patch_kernels(shape, epilogue):
+    """kw = 3, W >= 128, C_out tiles <= 128: the halo-row kernel loads each 130-pixel row
+    segment once and feeds the three dw taps through row-shifted UMMA descriptors; it must
+    match torch and the per-tap kernels (different tap order: agreement to rounding)."""
+    from opendwm_b200 import lib
+    tol = 8e-3 if epilogue == "store" else 1e-3
+    lib.set_option("conv_halo", 1)
+    try:
+        eh = _case(*shape, torch.float16, epilogue, seed=11)
+        yh = _LAST[0].float().clone()
+        lib.set_option("conv_halo", 0)
+        e2 = _case(*shape, torch.float16, epilogue, seed=11)
+        y2 = _LAST[0].float()
+    finally:
+        lib.set_option("conv_halo", 1)
+    assert eh < tol and e2 < tol, (eh, e2)
+    assert ((yh - y2).abs().max() / y2.abs().max()).item() < (2e-3 if epilogue == "store" else 2e-5)
