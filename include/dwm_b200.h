@@ -113,7 +113,12 @@ const char* dwm_b200_last_error(void);
  * keeps the register-resident kernel;
  * "resid_tma" = 1 (default) stages the fp32 residual tile of DWM_EPI_RESID through shared
  * memory with TMA loads and stores (2-CTA kernel, plain [M,N] residual), 0 keeps the
- * register / transposing epilogue. */
+ * register / transposing epilogue;
+ * "gemm_bn" = 0 (default) picks the RESID tile width by wave efficiency, 128 / 256 force it;
+ * "conv_2cta" = 1 (default) runs convolutions with >= 2 pixel tiles per SM on the
+ * cta_group::2 kernel, 0 on the 1-CTA kernel; "conv_halo" = 1 (default) routes kw = 3,
+ * W >= 128, C_out-tile <= 128 convolutions to the halo-row kernel (one load of a 130-pixel
+ * row segment serves the three dw taps), 0 to the per-tap kernels. */
 int dwm_b200_set_option(const char* name, int value);
 
 /* y = epilogue(A @ W^T): replaces every torch.nn.Linear / 1x1 / patchify conv on the

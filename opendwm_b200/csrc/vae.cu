@@ -134,10 +134,9 @@ struct SnParams {
   void* out; int out_T, out_t0;
 };
 
-// grid = (chunks, nb): a block works on SN_CHUNK float4 of ONE image, so the (mean, rstd) of its
+// grid = (chunks, nb): a block works on one chunk (16 float4 per thread) of ONE image, so the (mean, rstd) of its
 // G groups are finalised once per block from the fp64 sums (first G threads, shared memory)
 // instead of per thread — the fp64 divisions made the per-thread version XU-pipe bound.
-constexpr int SN_CHUNK = 4096;
 
 // Per-thread state is set up ONCE: with blockDim a multiple of C/4 a thread keeps the same
 // channel quad for all its elements, so gamma / beta / (mean, rstd) are registers, the pixel
@@ -147,9 +146,11 @@ constexpr int SN_CHUNK = 4096;
 // The r01 kernel spent ~10 integer divisions per float4 and ran at 18 % of DRAM peak
 // (profiles/r01_ncu_kernels_summary.txt); this one is a plain stream.
 template <typename T>
-__global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
+__global__ void __launch_bounds__(1024) spatialnorm_kernel(const SnParams p, const int chunk) {
+  // blockDim.x is a multiple of C/4 whenever C/4 <= 1024 (host side), `chunk` = blockDim.x * 16
   __shared__ float2 s_stat[64];
   __shared__ int s_tz[64];
+  const int NT = static_cast<int>(blockDim.x);
   const int vec = p.C >> 2;
   const int n = blockIdx.y;
   const int cg = p.C / p.G;
@@ -169,27 +170,30 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
                                      : (t * p.Tz) / p.T;
   }
   __syncthreads();
-  const long long i0 = static_cast<long long>(blockIdx.x) * SN_CHUNK;
-  long long i1 = i0 + SN_CHUNK;
+  const long long i0 = static_cast<long long>(blockIdx.x) * chunk;
+  long long i1 = i0 + chunk;
   if (i1 > per_img) i1 = per_img;
   const float4* xin = reinterpret_cast<const float4*>(p.x) + static_cast<long long>(n) * per_img;
   const float4* g4 = reinterpret_cast<const float4*>(p.gamma);
   const float4* b4 = reinterpret_cast<const float4*>(p.beta);
-  const bool fast = (256 % vec) == 0 && (SN_CHUNK % vec) == 0 && (cg & 3) == 0 && p.T <= 64;
+  const bool fast = (NT % vec) == 0 && (chunk % vec) == 0 && p.T <= 64;
   if (fast) {
     const int c4 = threadIdx.x % vec;
-    const int pstep = 256 / vec;                                  // pixels per iteration
+    const int pstep = NT / vec;                                   // pixels per iteration
     long long pix = i0 / vec + threadIdx.x / vec;                 // i0 % vec == 0
     int w = static_cast<int>(pix % p.W);
     long long r = pix / p.W;
     int h = static_cast<int>(r % p.H);
     int t = static_cast<int>(r / p.H);
     const float4 ga = __ldg(g4 + c4), be = __ldg(b4 + c4);
-    const float2 st = s_stat[(c4 * 4) / cg];
+    // the four channels of the quad may sit in different groups (UNet: 10 / 20 / 40 channels
+    // per group): one (mean, rstd) per element, all in registers
+    const float2 st0 = s_stat[(c4 * 4) / cg], st1 = s_stat[(c4 * 4 + 1) / cg];
+    const float2 st2 = s_stat[(c4 * 4 + 2) / cg], st3 = s_stat[(c4 * 4 + 3) / cg];
     // (x - mean) * (rstd * gamma) + beta: the subtraction stays first (no cancellation in a
     // pre-folded offset when |mean| >> std)
-    const float4 aa = make_float4(st.y * ga.x, st.y * ga.y, st.y * ga.z, st.y * ga.w);
-    const float mu = st.x;
+    const float4 aa = make_float4(st0.y * ga.x, st1.y * ga.y, st2.y * ga.z, st3.y * ga.w);
+    const float4 mu = make_float4(st0.x, st1.x, st2.x, st3.x);
     // latent-grid coordinates: shifts when H = hz << k (else a division per element)
     int hs = -1, ws = -1;
     if (p.zy) {
@@ -200,10 +204,10 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
     }
     const long long zn = static_cast<long long>(n) * p.Tz;
     const long long on = static_cast<long long>(n) * p.out_T + p.out_t0;
-    for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    for (long long i = i0 + threadIdx.x; i < i1; i += NT) {
       float4 v = xin[i];
-      v.x = fmaf(v.x - mu, aa.x, be.x); v.y = fmaf(v.y - mu, aa.y, be.y);
-      v.z = fmaf(v.z - mu, aa.z, be.z); v.w = fmaf(v.w - mu, aa.w, be.w);
+      v.x = fmaf(v.x - mu.x, aa.x, be.x); v.y = fmaf(v.y - mu.y, aa.y, be.y);
+      v.z = fmaf(v.z - mu.z, aa.z, be.z); v.w = fmaf(v.w - mu.w, aa.w, be.w);
       if (p.zy) {
         const int hq = hs >= 0 ? (h >> hs) : (h * p.hz) / p.H;
         const int wq = ws >= 0 ? (w >> ws) : (w * p.wz) / p.W;
@@ -222,8 +226,8 @@ __global__ void __launch_bounds__(256) spatialnorm_kernel(const SnParams p) {
     }
     return;
   }
-  // general path: any channel count / group size (UNet widths 320 / 640 / 1280 ...)
-  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+  // general path (C / 4 > 1024 or more than 64 frames)
+  for (long long i = i0 + threadIdx.x; i < i1; i += NT) {
     const int c4 = static_cast<int>(i % vec);
     long long r = i / vec;
     const int w = static_cast<int>(r % p.W); r /= p.W;
@@ -342,10 +346,16 @@ extern "C" int dwm_b200_spatialnorm_silu(const float* x, int64_t nb, int64_t T, 
   p.Tz = Tz; p.hz = hz; p.wz = wz; p.silu = apply_silu; p.out = out; p.out_T = (int)out_T; p.out_t0 = (int)out_t0;
   DWM_REQUIRE(groups <= 64 && nb <= 65535, "dwm_b200_spatialnorm_silu: groups <= 64 and nb <= 65535 required");
   const long long per_img = T * H * W * (C / 4);
-  dim3 grid(static_cast<unsigned>((per_img + SN_CHUNK - 1) / SN_CHUNK), static_cast<unsigned>(nb));
+  // block = the largest multiple of C/4 that fits 256 threads (or C/4 itself up to 1024), so a
+  // thread keeps one channel quad; 16 float4 per thread
+  const int vec = C / 4;
+  int threads = 256;
+  if (vec <= 1024) threads = vec <= 256 ? (256 / vec) * vec : vec;
+  const int chunk = threads * 16;
+  dim3 grid(static_cast<unsigned>((per_img + chunk - 1) / chunk), static_cast<unsigned>(nb));
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == DWM_BF16) spatialnorm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p);
-  else if (dtype == DWM_F16) spatialnorm_kernel<__half><<<grid, 256, 0, s>>>(p);
+  if (dtype == DWM_BF16) spatialnorm_kernel<__nv_bfloat16><<<grid, threads, 0, s>>>(p, chunk);
+  else if (dtype == DWM_F16) spatialnorm_kernel<__half><<<grid, threads, 0, s>>>(p, chunk);
   else { set_last_error("dwm_b200_spatialnorm_silu: bad dtype"); return -1; }
   DWM_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -429,6 +429,11 @@ class CrossviewTemporalSD:
         # (DWM_CUDA_GRAPH_SHARDED=1, not yet measured); multistep schedulers keep host state
         sharded = self.sharding is not None and \
             os.environ.get("DWM_CUDA_GRAPH_SHARDED", "0") != "1"
+        if self.sharding is not None and self.sharding.t_ways > 1 and \
+                len(getattr(self.model, "temporal_block_layers", ())) % 2 == 1:
+            # the peer K,V buffers alternate per temporal block; a captured step with an odd
+            # number of blocks would end and restart on the same buffer (no barrier in between)
+            sharded = True
         if sharded or stateful:
             return self.denoise_step(latents, conditions, idx, timesteps, in_range)
         key = (latents.data_ptr(), tuple(latents.shape), idx is None, in_range is None,
