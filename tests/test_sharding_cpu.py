@@ -218,3 +218,36 @@ def test_sharded_window_matches_unsharded_world2():
 
 def test_sharded_window_matches_unsharded_world4():
     _run(_sharded_window, 4)          # cfg2 x frames2, decode of 3 items over 4 ranks
+
+
+def _seed_broadcast(rank, world):
+    """Attaching a plan to a pipeline WITHOUT `generator_seed` makes every rank draw rank 0's
+    noise (`generator.seed()` seeds each rank differently and the CFG pair / frame
+    shards would silently denoise different latents); with a configured seed nothing changes."""
+    from dwm.pipelines.ctsd import CrossviewTemporalSD
+    from opendwm_b200.sharding import ShardPlan
+    plan = ShardPlan(world, rank, 4, cfg=True)
+    pipe = object.__new__(CrossviewTemporalSD)
+    pipe.config = {}
+    pipe.generator = torch.Generator()
+    pipe.generator.manual_seed(1000 + rank)               # stands for generator.seed()
+    pipe.sharding = plan
+    seeds = [None] * world
+    dist.all_gather_object(seeds, pipe.generator.initial_seed())
+    assert seeds == [1000] * world, seeds
+    noise = torch.randn(3, generator=pipe.generator)
+    got = [None] * world
+    dist.all_gather_object(got, noise.tolist())
+    assert all(g == got[0] for g in got)
+    pipe2 = object.__new__(CrossviewTemporalSD)
+    pipe2.config = {"generator_seed": 7}
+    pipe2.generator = torch.Generator()
+    pipe2.generator.manual_seed(7)
+    pipe2.sharding = plan
+    assert pipe2.generator.initial_seed() == 7
+    pipe2.sharding = None                                   # detaching is always allowed
+    assert pipe2.sharding is None
+
+
+def test_sharded_pipeline_broadcasts_the_seed_when_none_is_configured():
+    _run(_seed_broadcast, 2)

@@ -113,3 +113,31 @@ def test_encode_matches_oracle(frames):
     assert d.parameters.shape == ref.shape
     err = ((d.parameters.float() - ref).abs().max() / ref.abs().max()).item()
     assert err < 8e-3, err
+
+
+def test_from_pretrained_builds_the_encoder_when_the_checkpoint_has_one_cpu(tmp_path):
+    """diffusers' AutoencoderKLCogVideoX always has an encoder; the mirror builds (and strictly
+    loads) it whenever the checkpoint carries `encoder.*` weights, and stays decoder-only for a
+    decoder-only checkpoint."""
+    import json
+    import safetensors.torch
+    from dwm.models.cogvideox_vae import AutoencoderKLCogVideoX
+    full = AutoencoderKLCogVideoX(**CFG, with_encoder=True)
+    g = torch.Generator().manual_seed(3)
+    state = {k: torch.randn(v.shape, generator=g) for k, v in full.state_dict().items()}
+    for sub, keep in (("both", lambda k: True), ("dec", lambda k: k.startswith("decoder."))):
+        d = tmp_path / sub / "vae"
+        d.mkdir(parents=True)
+        with open(d / "config.json", "w") as f:
+            json.dump(dict(CFG, _class_name="AutoencoderKLCogVideoX", scaling_factor=1.15258426), f)
+        safetensors.torch.save_file({k: v for k, v in state.items() if keep(k)},
+                                    str(d / "diffusion_pytorch_model.safetensors"))
+    v = AutoencoderKLCogVideoX.from_pretrained(str(tmp_path / "both"), subfolder="vae")
+    assert hasattr(v, "encoder")
+    sd = v.state_dict()
+    assert set(sd) == set(state)
+    assert all(torch.equal(sd[k], state[k]) for k in state)
+    v2 = AutoencoderKLCogVideoX.from_pretrained(str(tmp_path / "dec"), subfolder="vae")
+    assert not hasattr(v2, "encoder")
+    assert torch.equal(v2.state_dict()["decoder.conv_in.conv.weight"],
+                       state["decoder.conv_in.conv.weight"])
