@@ -78,15 +78,16 @@ def frame_batch(g, V, hw, L, text_dim, pooled_dim, t):
     K = torch.zeros(1, 1, V, 3, 3)
     K[..., 0, 0] = K[..., 1, 1] = 500.0
     K[..., 0, 2], K[..., 1, 2], K[..., 2, 2] = hw[1] / 2, hw[0] / 2, 1.0
+    pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
     pose = torch.eye(4).view(1, 1, 1, 4, 4).clone()
     pose[..., 0, 3] = 0.8 * t
     ego = pose @ _rigid(torch.Generator().manual_seed(5), 1, 1, V + 2, scale=0.5)
     return {
         "pts": torch.full((1, 1, V), 100.0 * t), "fps": torch.tensor([10.0]),
-        "text_embeddings": (torch.randn(1, 1, V, L, text_dim, generator=g) * 0.1).pin_memory(),
+        "text_embeddings": pin(torch.randn(1, 1, V, L, text_dim, generator=g) * 0.1),
         "pooled_text_embeddings": torch.randn(1, 1, V, pooled_dim, generator=g),
-        "3dbox_images": torch.rand(1, 1, V, 3, *hw, generator=g).pin_memory(),
-        "hdmap_images": torch.rand(1, 1, V, 3, *hw, generator=g).pin_memory(),
+        "3dbox_images": pin(torch.rand(1, 1, V, 3, *hw, generator=g)),
+        "hdmap_images": pin(torch.rand(1, 1, V, 3, *hw, generator=g)),
         "crossview_mask": _ring(V).unsqueeze(0),
         "camera_intrinsics": K,
         "camera_transforms": _rigid(torch.Generator().manual_seed(6), 1, 1, V, scale=1.5),
