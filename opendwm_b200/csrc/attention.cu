@@ -20,7 +20,7 @@
 #include "../../include/dwm_b200.h"
 
 namespace dwm {
-extern int g_attn_tc;   // -1: from env, 0: mma.sync kernel only, 1 / 2: attention_tc.cu / attention_tc2.cu when eligible (gemm.cu)
+extern int g_attn_tc;   // -1: from env, 0: mma.sync kernel only, >= 1: attention_tc2.cu when eligible (gemm.cu)
 
 constexpr int HD = 64;
 

@@ -1,9 +1,10 @@
 // tcgen05 / TMEM flash attention, second generation: TWO co-resident CTAs per SM and the
 // running output kept in TMEM.
 //
-// attention_tc.cu is bound by its 4 softmax warps (one per SM sub-partition): every score
-// costs one MUFU ex2 plus ~4 issue slots, and a single warp per sub-partition cannot keep
-// the MUFU pipe full while it also moves P and folds P·V into a register accumulator.
+// A one-CTA-per-SM design (the first-generation kernel of round 1) is bound by its 4 softmax
+// warps (one per SM sub-partition): every score costs one MUFU ex2 plus ~4 issue slots, and a
+// single warp per sub-partition cannot keep the MUFU pipe full while it also moves P and folds
+// P·V into a register accumulator.
 // Here each CTA is slimmed down so that two fit on one SM (112 KB smem, 256 TMEM columns,
 // 128 registers/thread at launch, re-partitioned 40 / 216 with setmaxnreg): the sub-partitions see two softmax warps each, and one CTA's
 // tensor-core work overlaps the other's exponentials.

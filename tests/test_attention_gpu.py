@@ -127,7 +127,7 @@ def test_temporal(T, kind, W, tc_variant):
 @pytest.mark.parametrize("seq,N,heads", [(448, 5, 4), (129, 3, 2), (200, 7, 1), (640, 2, 3),
                                          (65, 4, 2), (602, 40, 24)])
 def test_contiguous_sequences_tcgen05(seq, N, heads, dtype, tc_variant):
-    """Contiguous unmasked groups take the tcgen05/TMEM kernel (attention_tc.cu)."""
+    """Contiguous unmasked groups take the tcgen05/TMEM kernel (attention_tc2.cu)."""
     from opendwm_b200 import ops
     D = heads * 64
     qkv = _qkv(N * seq, D, dtype, seed=seq)
