@@ -454,7 +454,11 @@ class CrossviewTemporalSD:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 self.denoise_step(latents, conditions, st["idx"], st["ts"], st["rng"])
-            # the entry keeps the keyed tensors alive (addresses are part of the key)
+            # the entry keeps the keyed tensors alive (addresses are part of the key); a new
+            # window / condition set means a new capture, so only the two most recent graphs
+            # (and their private memory pools) are kept
+            while len(graphs) >= 2:
+                graphs.pop(next(iter(graphs)))
             g = graphs[key] = (graph, st, (latents, dict(conditions)))
         graph, st = g[:2]
         if idx is not None:
