@@ -336,7 +336,7 @@ class CrossviewTemporalSD:
 
     @property
     def sharding(self):
-        return self._sharding
+        return getattr(self, "_sharding", None)
 
     @sharding.setter
     def sharding(self, plan):
