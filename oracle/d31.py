@@ -6,7 +6,9 @@ neither vendored under /root/reference nor installed here, so these classes
 restate the published algorithm of that release and are
 anchored on the reference's own call sites (cited per class).
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+PARITY UNPINNED (tools/pin_diffusers.py pins it the moment diffusers==0.31.0 is importable:
+it re-runs the reference on the real package and diffs every golden): the reference ships no
+tests, golden vectors or fixtures for
 this path and cannot be imported here, so this oracle is
 checked for internal consistency only.  Parameter names follow the diffusers
 state_dict keys so real checkpoints load unchanged.  (These classes
